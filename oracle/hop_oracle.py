@@ -1,0 +1,297 @@
+"""CPU restatement of Hawkeye's high-order-pooling hot path (TEST INFRASTRUCTURE ONLY).
+
+This is the parity ORACLE, not product code.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import it; nothing under ``hawkeye_b200/`` does, and the product fails
+loudly when its CUDA library is missing rather than routing here.
+
+Pinning: the reference ships no tests or golden vectors, so the
+oracle is pinned by (a) ``tests/golden/*.npz`` — outputs of the UNMODIFIED
+reference modules imported from /root/reference by ``tests/golden/make_golden.py``
+— and (b) the numpy-RNG known answers for the count-sketch hashes
+(``tests/test_oracle.py``).  Every function cites the reference lines it restates.
+All arithmetic is numpy / torch-CPU; ``dtype`` selects fp32 (the reference's
+precision) or fp64 (to separate our error from the reference's own rounding).
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------
+# BCNN bilinear pooling  (model/methods/BCNN.py:13-27)
+# --------------------------------------------------------------------------------------
+
+
+def bilinear_pool_fwd(x):
+    """x: [B,C,H,W] -> [B,C*C].  bmm(x,xT)/HW (:17-18); sqrt(.+1e-5) (:21); F.normalize (:26)."""
+    B, C = x.shape[0], x.shape[1]
+    hw = x.shape[2] * x.shape[3]
+    xf = x.reshape(B, C, hw)
+    g = torch.bmm(xf, xf.transpose(1, 2)) / hw
+    z = torch.sqrt(g.reshape(B, -1) + 1e-5)
+    n = z.norm(dim=1, keepdim=True).clamp_min(1e-12)  # F.normalize: x / max(||x||_2, eps)
+    return z / n
+
+
+def bilinear_pool_bwd(x, dy):
+    """Closed-form input gradient of BCNN.py:13-27 (what autograd derives).
+
+    dz=(dy - y<y,dy>)/||z||; dG=dz/(2z); dX=(dG+dG^T) X / HW.
+    """
+    B, C = x.shape[0], x.shape[1]
+    hw = x.shape[2] * x.shape[3]
+    xf = x.reshape(B, C, hw)
+    g = torch.bmm(xf, xf.transpose(1, 2)) / hw
+    z = torch.sqrt(g.reshape(B, -1) + 1e-5)
+    n = z.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    y = z / n
+    dz = (dy - y * (y * dy).sum(1, keepdim=True)) / n
+    dg = (dz / (2 * z)).reshape(B, C, C)
+    dx = torch.bmm(dg + dg.transpose(1, 2), xf) / hw
+    return dx.reshape_as(x)
+
+
+# --------------------------------------------------------------------------------------
+# CBCNN compact bilinear pooling  (model/methods/CBCNN.py:38-164)
+# --------------------------------------------------------------------------------------
+
+
+def cbp_hashes(input_dim, output_dim):
+    """Count-sketch hash/sign vectors, bit-exact contract (CBCNN.py:76-91).
+
+    numpy legacy global MT19937 stream: seed(1)->h1, seed(3)->s1, seed(5)->h2, seed(7)->s2.
+    Returns int64 arrays (h1, s1, h2, s2).
+    """
+    np.random.seed(1)
+    h1 = np.random.randint(output_dim, size=input_dim)
+    np.random.seed(3)
+    s1 = 2 * np.random.randint(2, size=input_dim) - 1
+    np.random.seed(5)
+    h2 = np.random.randint(output_dim, size=input_dim)
+    np.random.seed(7)
+    s2 = 2 * np.random.randint(2, size=input_dim) - 1
+    return (h1.astype(np.int64), s1.astype(np.int64), h2.astype(np.int64), s2.astype(np.int64))
+
+
+def sketch_matrix(h, s, output_dim, dtype=torch.float32):
+    """Dense [input_dim, output_dim] one-hot*sign matrix (CBCNN.py:137-164)."""
+    m = torch.zeros(len(h), output_dim, dtype=dtype)
+    m[torch.arange(len(h)), torch.from_numpy(np.asarray(h))] = torch.from_numpy(np.asarray(s)).to(dtype)
+    return m
+
+
+def cbp_fwd(x, output_dim, hashes=None):
+    """x: [B,C,H,W] -> [B,d].  The reference's FFT route (CBCNN.py:96-135)."""
+    B, C, H, W = x.shape
+    h1, s1, h2, s2 = hashes if hashes is not None else cbp_hashes(C, output_dim)
+    S1 = sketch_matrix(h1, s1, output_dim, x.dtype)
+    S2 = sketch_matrix(h2, s2, output_dim, x.dtype)
+    flat = x.permute(0, 2, 3, 1).contiguous().view(-1, C)          # :114
+    sk1, sk2 = flat.mm(S1), flat.mm(S2)                             # :117-118
+    prod = torch.fft.fft(sk1) * torch.fft.fft(sk2)                  # :120-123
+    cbp = torch.fft.ifft(prod).real.view(B, H, W, output_dim)       # :125-127
+    cbp = cbp.sum(dim=1).sum(dim=1)                                 # :130
+    cbp = torch.sign(cbp) * torch.sqrt(torch.abs(cbp) + 1e-10)      # :132
+    return F.normalize(cbp)                                         # :133
+
+
+def cbp_presqrt_gram_scatter(x, output_dim, hashes=None):
+    """Identity cross-check: sum_p ifft(fft(xS1)*fft(xS2)) ==
+    signed scatter of the un-normalised Gram  X X^T  into bins (h1[i]+h2[j]) mod d."""
+    B, C, H, W = x.shape
+    h1, s1, h2, s2 = hashes if hashes is not None else cbp_hashes(C, output_dim)
+    xf = x.reshape(B, C, H * W)
+    g = torch.bmm(xf, xf.transpose(1, 2))
+    idx = torch.from_numpy((h1[:, None] + h2[None, :]) % output_dim).reshape(-1)
+    sgn = torch.from_numpy((s1[:, None] * s2[None, :])).to(x.dtype).reshape(-1)
+    out = torch.zeros(B, output_dim, dtype=x.dtype)
+    out.index_add_(1, idx, g.reshape(B, -1) * sgn)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Fast MPN-COV  (model/methods/MPNCOV.py:105-230)
+# --------------------------------------------------------------------------------------
+
+
+def covpool_fwd(x):
+    """Covpool.forward (MPNCOV.py:107-119): X I_hat X^T, I_hat = I/M - 11^T/M^2."""
+    B, C = x.shape[0], x.shape[1]
+    M = x.shape[2] * x.shape[3]
+    xf = x.reshape(B, C, M)
+    I_hat = (-1.0 / M / M) * torch.ones(M, M, dtype=x.dtype) + (1.0 / M) * torch.eye(M, dtype=x.dtype)
+    return xf.matmul(I_hat).bmm(xf.transpose(1, 2))
+
+
+def covpool_bwd(x, g):
+    """Covpool.backward (MPNCOV.py:121-134): (g+g^T) X I_hat."""
+    B, C = x.shape[0], x.shape[1]
+    M = x.shape[2] * x.shape[3]
+    xf = x.reshape(B, C, M)
+    I_hat = (-1.0 / M / M) * torch.ones(M, M, dtype=x.dtype) + (1.0 / M) * torch.eye(M, dtype=x.dtype)
+    return (g + g.transpose(1, 2)).bmm(xf).matmul(I_hat).reshape_as(x)
+
+
+def sqrtm_fwd(x, iterN):
+    """Sqrtm.forward (MPNCOV.py:139-164).  Returns (y, saved) with saved=(A, YZY, normA, Y, Z)."""
+    B, dim = x.shape[0], x.shape[1]
+    I3 = 3.0 * torch.eye(dim, dtype=x.dtype).expand(B, dim, dim)
+    normA = (1.0 / 3.0) * (x * I3).sum(dim=1).sum(dim=1)
+    A = x / normA.view(B, 1, 1)
+    Y = torch.zeros(B, iterN, dim, dim, dtype=x.dtype)
+    Z = torch.eye(dim, dtype=x.dtype).view(1, 1, dim, dim).repeat(B, iterN, 1, 1)
+    if iterN < 2:
+        ZY = 0.5 * (I3 - A)
+        YZY = A.bmm(ZY)
+    else:
+        ZY = 0.5 * (I3 - A)
+        Y[:, 0] = A.bmm(ZY)
+        Z[:, 0] = ZY
+        for i in range(1, iterN - 1):
+            ZY = 0.5 * (I3 - Z[:, i - 1].bmm(Y[:, i - 1]))
+            Y[:, i] = Y[:, i - 1].bmm(ZY)
+            Z[:, i] = ZY.bmm(Z[:, i - 1])
+        YZY = 0.5 * Y[:, iterN - 2].bmm(I3 - Z[:, iterN - 2].bmm(Y[:, iterN - 2]))
+    y = YZY * torch.sqrt(normA).view(B, 1, 1)
+    return y, (A, YZY, normA, Y, Z)
+
+
+def sqrtm_bwd(x, saved, g, iterN):
+    """Sqrtm.backward (MPNCOV.py:166-202), the reference's hand-derived formulae verbatim in order."""
+    A, ZYs, normA, Y, Z = saved
+    B, dim = x.shape[0], x.shape[1]
+    P = g * torch.sqrt(normA).view(B, 1, 1)
+    aux = (g * ZYs).sum(dim=1).sum(dim=1) / (2 * torch.sqrt(normA))
+    I3 = 3.0 * torch.eye(dim, dtype=x.dtype).expand(B, dim, dim)
+    if iterN < 2:
+        D = 0.5 * (P.bmm(I3 - A) - A.bmm(P))
+    else:
+        Yl, Zl = Y[:, iterN - 2], Z[:, iterN - 2]
+        dldY = 0.5 * (P.bmm(I3 - Yl.bmm(Zl)) - Zl.bmm(Yl).bmm(P))
+        dldZ = -0.5 * Yl.bmm(P).bmm(Yl)
+        for i in range(iterN - 3, -1, -1):
+            YZ = I3 - Y[:, i].bmm(Z[:, i])
+            ZY = Z[:, i].bmm(Y[:, i])
+            dldY_ = 0.5 * (dldY.bmm(YZ) - Z[:, i].bmm(dldZ).bmm(Z[:, i]) - ZY.bmm(dldY))
+            dldZ_ = 0.5 * (YZ.bmm(dldZ) - Y[:, i].bmm(dldY).bmm(Y[:, i]) - dldZ.bmm(ZY))
+            dldY, dldZ = dldY_, dldZ_
+        D = 0.5 * (dldY.bmm(I3 - A) - dldZ - A.bmm(dldY))
+    D = D.transpose(1, 2)                                            # :195
+    gx = D / normA.view(B, 1, 1)                                     # :196
+    gaux = (D * x).sum(dim=1).sum(dim=1)                             # :197
+    coef = aux - gaux / (normA * normA)                              # :198-201
+    gx = gx + coef.view(B, 1, 1) * torch.eye(dim, dtype=x.dtype)
+    return gx
+
+
+def triuvec_index(dim):
+    """Row-major positions of ones(dim,dim).triu() (MPNCOV.py:213-214)."""
+    return torch.ones(dim, dim).triu().reshape(-1).nonzero().reshape(-1)
+
+
+def triuvec_fwd(x):
+    """Triuvec.forward (MPNCOV.py:207-218) -> [B, dim(dim+1)/2, 1]."""
+    B, dim = x.shape[0], x.shape[1]
+    return x.reshape(B, dim * dim)[:, triuvec_index(dim)].unsqueeze(-1)
+
+
+def triuvec_bwd(g, dim):
+    """Triuvec.backward (MPNCOV.py:220-230)."""
+    B = g.shape[0]
+    out = torch.zeros(B, dim * dim, dtype=g.dtype)
+    out[:, triuvec_index(dim)] = g.reshape(B, -1)
+    return out.reshape(B, dim, dim)
+
+
+def mpncov_pool_fwd(x, iterN=5):
+    """cov -> sqrtm -> triuvec on a [B,C,H,W] (already dimension-reduced) feature (MPNCOV.py:97-101)."""
+    c = covpool_fwd(x)
+    y, saved = sqrtm_fwd(c, iterN)
+    return triuvec_fwd(y), (c, saved)
+
+
+def mpncov_pool_bwd(x, g, iterN=5):
+    c = covpool_fwd(x)
+    _, saved = sqrtm_fwd(c, iterN)
+    gs = triuvec_bwd(g, c.shape[1])
+    gc = sqrtm_bwd(c, saved, gs, iterN)
+    return covpool_bwd(x, gc)
+
+
+# --------------------------------------------------------------------------------------
+# VGG-16 "D" features  (model/backbone/vgg.py:56-70,76) and the BCNN / CBCNN heads
+# --------------------------------------------------------------------------------------
+
+VGG16_D = [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M']
+
+
+def vgg_cfg_scaled(width_div=1):
+    """VGG16_D with channel widths divided (for small parity cases); width_div=1 is the reference."""
+    return [v if v == 'M' else max(v // width_div, 8) for v in VGG16_D]
+
+
+def vgg_state_keys(cfg=VGG16_D):
+    """Sequential indices of the conv layers: backbone.{0,2,5,...}.{weight,bias}."""
+    keys, idx = [], 0
+    for v in cfg:
+        if v == 'M':
+            idx += 1
+        else:
+            keys.append(idx)
+            idx += 2
+    return keys
+
+
+def vgg_features_fwd(x, state, cfg=VGG16_D, prefix='backbone.'):
+    """conv3x3(s1,p1)+bias -> ReLU, 'M' = MaxPool2d(2,2) (vgg.py:56-70)."""
+    idx = 0
+    for v in cfg:
+        if v == 'M':
+            x = F.max_pool2d(x, 2, 2)
+            idx += 1
+        else:
+            x = F.relu(F.conv2d(x, state[f'{prefix}{idx}.weight'], state[f'{prefix}{idx}.bias'], padding=1))
+            idx += 2
+    return x
+
+
+def cross_entropy_ls(logits, labels, smoothing=0.1):
+    """nn.CrossEntropyLoss(label_smoothing=0.1) (train.py:211-212), mean reduction."""
+    return F.cross_entropy(logits, labels, label_smoothing=smoothing)
+
+
+def bcnn_forward(x, state, stage=2, cfg=VGG16_D):
+    """BCNN.forward (BCNN.py:49-55)."""
+    f = vgg_features_fwd(x, state, cfg)
+    if stage == 1:
+        f = f.detach()
+    y = bilinear_pool_fwd(f)
+    return F.linear(y, state['classifier.weight'], state['classifier.bias'])
+
+
+def cbcnn_forward(x, state, output_dim, stage=2, cfg=VGG16_D):
+    """CBCNN.forward (CBCNN.py:29-35)."""
+    f = vgg_features_fwd(x, state, cfg)
+    if stage == 1:
+        f = f.detach()
+    y = cbp_fwd(f, output_dim)
+    return F.linear(y, state['classifier.weight'], state['classifier.bias'])
+
+
+def loss_and_grads(forward_fn, x, labels, state, train_keys=None):
+    """loss = CE_ls(forward(x)); returns (logits, loss, {param: grad}) via torch-CPU autograd over the
+    restated forward — the same thing the reference's loss.backward() (train.py:315-319) computes."""
+    st = {k: v.detach().clone().requires_grad_(train_keys is None or k in train_keys) for k, v in state.items()}
+    logits = forward_fn(x, st)
+    loss = cross_entropy_ls(logits, labels)
+    params = [v for v in st.values() if v.requires_grad]
+    grads = torch.autograd.grad(loss, params, allow_unused=True)
+    names = [k for k, v in st.items() if v.requires_grad]
+    return logits.detach(), loss.detach(), dict(zip(names, grads))
+
+
+def sgd_momentum_step(p, g, buf, lr, momentum, weight_decay, first):
+    """torch.optim.SGD (Examples/BCNN.py:40): g+=wd*p; buf = g (first) | m*buf+g; p-=lr*buf."""
+    g = g + weight_decay * p
+    buf = g.clone() if first else momentum * buf + g
+    return p - lr * buf, buf
