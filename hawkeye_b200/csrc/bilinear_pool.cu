@@ -1,0 +1,391 @@
+// Fused bilinear (second-order) pooling kernels.
+//
+// Reference semantics (model/methods/BCNN.py:13-27):
+//     G = X X^T / HW ; z = sqrt(G + 1e-5) ; y = z / max(||z||_2, 1e-12)          X: [B, C, HW]
+// and for compact bilinear pooling (model/methods/CBCNN.py:96-135) the Tensor-Sketch of the
+// un-normalised Gram, which equals the signed scatter  out[(h1[i]+h2[j]) mod d] += s1[i] s2[j] (X X^T)[i][j].
+//
+// Design (B200): the C x C Gram runs on tcgen05 (kind::tf32, fp32 accumulate in TMEM); X tiles are
+// staged by TMA into 128B-swizzled shared memory straight from the NCHW feature map (HW is the
+// K dimension, zero-filled to a multiple of 8 by TMA).  Work item = one CTA = a *pair* of 128x128
+// Gram tiles sharing the same two 128-row blocks of X:
+//     off-diagonal pair (bi<bj):  acc0 = X_bi X_bj^T , acc1 = X_bj X_bi^T   (same smem, swapped descriptors)
+//     diagonal pair             :  acc0 = X_b0 X_b0^T , acc1 = X_b1 X_b1^T
+// Each accumulator (lane = row of the A block, column = row of the B block) is written to the
+// *transposed* output block — legal because G is symmetric — so the 32 lanes of a warp store 32
+// consecutive floats (128 B, fully coalesced) with no shared-memory staging.
+// The L2 norm is obtained in closed form before any tile is written:
+//     ||z||^2 = sum_p (sum_c x_cp)^2 / HW + C^2 * 1e-5
+// from per-location channel sums produced by a tiny pre-kernel (K0), so Y is written exactly once.
+#include "common.cuh"
+#include "host.h"
+#include "../../include/hawkeye_b200.h"
+
+namespace hk {
+
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// ---------------------------------------------------------------- K0: per-location channel-sum partials
+// partial[b][cs][p] = sum_{c in split cs} x[b][c][p];  also zeroes the per-image scalars used by the backward.
+__global__ void colsum_partial_kernel(const float* __restrict__ X, float* __restrict__ partial, int C, int HW, int CS,
+                                      float* zero_a, float* zero_b, int zero_n) {
+  const int b = blockIdx.x, cs = blockIdx.y;
+  if (cs == 0 && threadIdx.x < zero_n) {
+    if (zero_a) zero_a[b * zero_n + threadIdx.x] = 0.f;
+    if (zero_b) zero_b[b * zero_n + threadIdx.x] = 0.f;
+  }
+  const int cper = (C + CS - 1) / CS;
+  const int c0 = cs * cper, c1 = min(C, c0 + cper);
+  const float* xb = X + (size_t)b * C * HW;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int c = c0; c < c1; ++c) s += xb[(size_t)c * HW + p];
+    partial[((size_t)b * CS + cs) * HW + p] = s;
+  }
+}
+
+enum { MODE_BCNN_FWD = 0, MODE_BCNN_BWD_S = 1, MODE_CBP_FWD = 2 };
+
+struct GramArgs {
+  int B, C, HW, nblk;
+  float inv_hw, eps;
+  const float* partial;  // [B][CS][HW]
+  int CS;
+  float* Y;              // mode 0: [B][C*C]
+  float* inv_norm;       // mode 0: written [B]; mode 1: read [B]
+  const float* dY;       // mode 1
+  float* S;              // mode 1: [B][C][C]
+  float* c_raw;          // mode 1: [B] (pre-zeroed)
+  const int* h1;         // mode 2
+  const int* h2;
+  const float* s1;
+  const float* s2;
+  float* bins;           // mode 2: [B][d] (pre-zeroed)
+  int d;
+};
+
+constexpr int GRAM_STAGES = 3;
+constexpr int GRAM_SLOT = 128 * 128;              // 16 KB: 128 rows x 32 fp32
+constexpr int GRAM_STAGE_BYTES = 2 * GRAM_SLOT;   // two row blocks per stage
+constexpr int GRAM_SMEM = GRAM_STAGES * GRAM_STAGE_BYTES + 1024 + 256;
+
+template <int MODE>
+__global__ void __launch_bounds__(192, 2) gram_pair_kernel(const __grid_constant__ CUtensorMap tmX, GramArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + GRAM_STAGES * GRAM_STAGE_BYTES);
+  uint64_t* empty = full + GRAM_STAGES;
+  uint64_t* accf = empty + GRAM_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
+  float* red = reinterpret_cast<float*>(tmem_slot + 1);  // 4 floats + 1 result
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  // ---- decode the work item into two row blocks
+  const int n_off = a.nblk * (a.nblk - 1) / 2;
+  int blk0, blk1, diag;
+  {
+    int t = blockIdx.x;
+    if (t < n_off) {
+      diag = 0;
+      int i = 0;
+      while (t >= a.nblk - 1 - i) { t -= a.nblk - 1 - i; ++i; }
+      blk0 = i; blk1 = i + 1 + t;
+    } else {
+      diag = 1;
+      blk0 = 2 * (t - n_off);
+      blk1 = (blk0 + 1 < a.nblk) ? blk0 + 1 : -1;
+    }
+  }
+  const int nacc = (blk1 >= 0) ? 2 : 1;
+  const int nk = (a.HW + 31) / 32;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < GRAM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accf, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % GRAM_STAGES;
+        const uint32_t ph = (kb / GRAM_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], nacc * GRAM_SLOT);
+        uint8_t* st = smem + s * GRAM_STAGE_BYTES;
+        tma_load_3d(st, &tmX, &full[s], kb * 32, blk0 * 128, b);
+        if (blk1 >= 0) tma_load_3d(st + GRAM_SLOT, &tmX, &full[s], kb * 32, blk1 * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, 128, 0, 0);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % GRAM_STAGES;
+        const uint32_t ph = (kb / GRAM_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t s0 = smem_u32(smem + s * GRAM_STAGE_BYTES);
+        const uint32_t s1 = s0 + GRAM_SLOT;
+        const int krem = a.HW - kb * 32;
+        const int ksteps = krem >= 32 ? 4 : (krem + 7) / 8;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t d0 = make_sdesc(s0 + ks * 32, 16, 1024);
+          const uint64_t d1 = make_sdesc(s1 + ks * 32, 16, 1024);
+          const uint32_t accum = (kb | ks) ? 1u : 0u;
+          if (diag) {
+            umma_tf32_ss(tmem_base, d0, d0, idesc, accum);
+            if (blk1 >= 0) umma_tf32_ss(tmem_base + 128, d1, d1, idesc, accum);
+          } else {
+            umma_tf32_ss(tmem_base, d0, d1, idesc, accum);        // acc0 = X_blk0 X_blk1^T
+            umma_tf32_ss(tmem_base + 128, d1, d0, idesc, accum);  // acc1 = X_blk1 X_blk0^T
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accf);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (128 threads)
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;  // 0..127
+    float inv_norm = 1.f;
+    if (MODE == MODE_BCNN_FWD) {
+      // closed-form norm from the channel-sum partials, overlapped with the TMA/MMA pipeline
+      float acc = 0.f;
+      const float* pb = a.partial + (size_t)b * a.CS * a.HW;
+      for (int p = et; p < a.HW; p += 128) {
+        float s = 0.f;
+        for (int cs = 0; cs < a.CS; ++cs) s += pb[cs * a.HW + p];
+        acc = fmaf(s, s, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) red[q] = acc;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float tot = red[0] + red[1] + red[2] + red[3];
+      const float nrm = sqrtf(tot * a.inv_hw + (float)a.C * (float)a.C * a.eps);
+      inv_norm = 1.f / fmaxf(nrm, 1e-12f);
+      if (blockIdx.x == 0 && et == 0 && a.inv_norm) a.inv_norm[b] = inv_norm;
+    }
+    mbar_wait(accf, 0);
+    tc_fence_after();
+    float craw = 0.f;
+    const size_t CC = (size_t)a.C * a.C;
+    for (int ac = 0; ac < nacc; ++ac) {
+      int ablk, bblk;
+      if (diag) { ablk = bblk = (ac == 0 ? blk0 : blk1); }
+      else      { ablk = (ac == 0 ? blk0 : blk1); bblk = (ac == 0 ? blk1 : blk0); }
+      const int ia = ablk * 128 + q * 32 + lane;  // row of the A block held by this thread
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ac * 128 + c * 32, v);
+        tmem_ld_wait();
+        const int jb0 = bblk * 128 + c * 32;
+        if (MODE == MODE_BCNN_FWD) {
+          float* y = a.Y + (size_t)b * CC + (size_t)jb0 * a.C + ia;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[(size_t)j * a.C] = tf32_round(fast_sqrt(fmaf(v[j], a.inv_hw, a.eps)) * inv_norm);
+        } else if (MODE == MODE_BCNN_BWD_S) {
+          const float* dyt = a.dY + (size_t)b * CC + (size_t)jb0 * a.C + ia;   // dY[jb][ia]: coalesced over lanes
+          const float4* dyd = reinterpret_cast<const float4*>(a.dY + (size_t)b * CC + (size_t)ia * a.C + jb0);
+          float* s = a.S + (size_t)b * CC + (size_t)jb0 * a.C + ia;
+          float dd[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = dyd[j];
+            dd[4 * j] = t.x; dd[4 * j + 1] = t.y; dd[4 * j + 2] = t.z; dd[4 * j + 3] = t.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float z = fast_sqrt(fmaf(v[j], a.inv_hw, a.eps));
+            const float dt = dyt[(size_t)j * a.C];
+            craw = fmaf(dt, z, craw);
+            s[(size_t)j * a.C] = tf32_round(__fdividef(dt + dd[j], 2.f * z));
+          }
+        } else {  // MODE_CBP_FWD: signed scatter of the raw Gram into the d sketch bins
+          const int hi = a.h1[ia];
+          const float si = a.s1[ia];
+          float* bins = a.bins + (size_t)b * a.d;
+#pragma unroll 8
+          for (int j = 0; j < 32; ++j) {
+            int bin = hi + a.h2[jb0 + j];
+            if (bin >= a.d) bin -= a.d;
+            atomicAdd(&bins[bin], si * a.s2[jb0 + j] * v[j]);
+          }
+        }
+      }
+    }
+    if (MODE == MODE_BCNN_BWD_S) {
+      craw = warp_sum(craw);
+      if (lane == 0) atomicAdd(&a.c_raw[b], craw);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+static int make_x_map(CUtensorMap* tm, const float* X, int B, int C, int HW) {
+  uint64_t dims[3] = {(uint64_t)HW, (uint64_t)C, (uint64_t)B};
+  uint64_t strides[2] = {(uint64_t)HW * 4, (uint64_t)C * HW * 4};
+  uint32_t box[3] = {32, 128, 1};
+  return make_tmap(tm, X, 3, dims, strides, box);
+}
+
+template <int MODE>
+static int launch_gram(const CUtensorMap& tm, const GramArgs& a, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gram_pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM);
+    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(gram): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int items = a.nblk * (a.nblk - 1) / 2 + (a.nblk + 1) / 2;
+  gram_pair_kernel<MODE><<<dim3(items, a.B), 192, GRAM_SMEM, stream>>>(tm, a);
+  HK_LAUNCH_CHECK("gram_pair_kernel");
+  return 0;
+}
+
+static int check_gram_shape(const char* op, const float* X, int B, int C, int HW) {
+  HK_REQUIRE(X, HK_ERR_ARG, "%s: null input", op);
+  HK_REQUIRE(B > 0 && B <= 65535 && C > 0 && HW > 0, HK_ERR_ARG, "%s: bad shape B=%d C=%d HW=%d", op, B, C, HW);
+  HK_REQUIRE(C % 128 == 0, HK_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of 128", op, C);
+  HK_REQUIRE(HW % 4 == 0, HK_ERR_UNSUPPORTED, "%s: H*W=%d must be a multiple of 4 (16-byte TMA row pitch)", op, HW);
+  HK_REQUIRE(aligned16(X), HK_ERR_ALIGN, "%s: input not 16-byte aligned", op);
+  return 0;
+}
+
+constexpr int COLSUM_SPLITS = 8;
+
+// per-batch scalars for the bilinear backward epilogue:  alpha = 1/(n HW),  beta = -(c_raw/n^2) / (n HW)
+__global__ void bilinear_bwd_scalars_kernel(const float* inv_norm, const float* c_raw, float inv_hw, float* alpha,
+                                            float* beta, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    const float in = inv_norm[b];
+    alpha[b] = in * inv_hw;
+    beta[b] = -(c_raw[b] * in * in) * in * inv_hw;
+  }
+}
+
+// s[b][p] = sum over splits of partial
+__global__ void colsum_finish_kernel(const float* partial, float* s, int CS, int HW) {
+  const int b = blockIdx.x;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    float t = 0.f;
+    for (int cs = 0; cs < CS; ++cs) t += partial[((size_t)b * CS + cs) * HW + p];
+    s[(size_t)b * HW + p] = t;
+  }
+}
+
+__global__ void norm_from_s_kernel(const float* s, float* inv_norm, int C, int HW) {
+  const int b = blockIdx.x;
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const float v = s[(size_t)b * HW + p];
+    acc = fmaf(v, v, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    const float nrm = sqrtf(t / (float)HW + (float)C * (float)C * 1e-5f);
+    inv_norm[b] = 1.f / fmaxf(nrm, 1e-12f);
+  }
+}
+
+int gemm_tf32(const float* A, int a_mn, long long lda, long long strideA, const float* B, int b_mn, long long ldb,
+              long long strideB, const struct GemmEpi& epi, int M, int N, int K, int batch, cudaStream_t stream);
+
+}  // namespace hk
+
+using namespace hk;
+
+extern "C" {
+
+size_t hk_bilinear_pool_fwd_workspace_bytes(int B, int C, int HW) {
+  (void)C;
+  return ((size_t)B * COLSUM_SPLITS * HW + B) * sizeof(float);
+}
+
+int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, int C, int HW, void* workspace,
+                         size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int r = check_gram_shape("hk_bilinear_pool_fwd", x, B, C, HW);
+  if (r) return r;
+  HK_REQUIRE(y && aligned16(y), HK_ERR_ALIGN, "hk_bilinear_pool_fwd: output null/unaligned");
+  HK_REQUIRE(workspace && workspace_bytes >= hk_bilinear_pool_fwd_workspace_bytes(B, C, HW), HK_ERR_WORKSPACE,
+             "hk_bilinear_pool_fwd: workspace too small");
+  float* partial = static_cast<float*>(workspace);
+  float* invn = inv_norm_out ? inv_norm_out : partial + (size_t)B * COLSUM_SPLITS * HW;
+  CUtensorMap tm;
+  if ((r = make_x_map(&tm, x, B, C, HW))) return r;
+  colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, 0, stream>>>(x, partial, C, HW, COLSUM_SPLITS, nullptr, nullptr, 0);
+  HK_LAUNCH_CHECK("colsum_partial_kernel");
+  GramArgs a = {};
+  a.B = B; a.C = C; a.HW = HW; a.nblk = C / 128;
+  a.inv_hw = 1.f / (float)HW; a.eps = 1e-5f;
+  a.partial = partial; a.CS = COLSUM_SPLITS;
+  a.Y = y; a.inv_norm = invn;
+  return launch_gram<MODE_BCNN_FWD>(tm, a, stream);
+}
+
+size_t hk_bilinear_pool_bwd_workspace_bytes(int B, int C, int HW) {
+  // S [B,C,C] + partial [B,CS,HW] + s [B,HW] + inv_norm,c_raw,alpha,beta [4B]
+  return ((size_t)B * C * C + (size_t)B * COLSUM_SPLITS * HW + (size_t)B * HW + 4 * (size_t)B + 64) * sizeof(float);
+}
+
+int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int C, int HW, void* workspace,
+                         size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int r = check_gram_shape("hk_bilinear_pool_bwd", x, B, C, HW);
+  if (r) return r;
+  HK_REQUIRE(dy && dx && aligned16(dy) && aligned16(dx), HK_ERR_ALIGN, "hk_bilinear_pool_bwd: null/unaligned pointer");
+  HK_REQUIRE(workspace && workspace_bytes >= hk_bilinear_pool_bwd_workspace_bytes(B, C, HW), HK_ERR_WORKSPACE,
+             "hk_bilinear_pool_bwd: workspace too small");
+  float* S = static_cast<float*>(workspace);
+  float* partial = S + (size_t)B * C * C;
+  float* svec = partial + (size_t)B * COLSUM_SPLITS * HW;
+  float* invn = svec + (size_t)B * HW;
+  float* craw = invn + B;
+  float* alpha = craw + B;
+  float* beta = alpha + B;
+  CUtensorMap tm;
+  if ((r = make_x_map(&tm, x, B, C, HW))) return r;
+  colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, 0, stream>>>(x, partial, C, HW, COLSUM_SPLITS, craw, nullptr, 1);
+  HK_LAUNCH_CHECK("colsum_partial_kernel");
+  // s_p = sum_c x_cp (also the rank-1 correction vector of the backward); the norm follows in closed form
+  colsum_finish_kernel<<<B, 256, 0, stream>>>(partial, svec, COLSUM_SPLITS, HW);
+  HK_LAUNCH_CHECK("colsum_finish_kernel");
+  GramArgs a = {};
+  a.B = B; a.C = C; a.HW = HW; a.nblk = C / 128;
+  a.inv_hw = 1.f / (float)HW; a.eps = 1e-5f;
+  a.dY = dy; a.S = S; a.c_raw = craw;
+  if ((r = launch_gram<MODE_BCNN_BWD_S>(tm, a, stream))) return r;
+  norm_from_s_kernel<<<B, 256, 0, stream>>>(svec, invn, C, HW);
+  HK_LAUNCH_CHECK("norm_from_s_kernel");
+  bilinear_bwd_scalars_kernel<<<(B + 127) / 128, 128, 0, stream>>>(invn, craw, 1.f / (float)HW, alpha, beta, B);
+  HK_LAUNCH_CHECK("bilinear_bwd_scalars_kernel");
+  // dX = alpha_b * (S . X) + beta_b * 1 s^T      (M=C, K=C, N=HW; X is the MN-major B operand)
+  return hk_gemm_tf32(S, 0, C, (long long)C * C, x, 1, HW, (long long)C * HW, dx, HW, (long long)C * HW, 0, C, HW, C, B,
+                      1.f, alpha, 0.f, svec, 0, HW, 1.f, beta, 0, stream_);
+}
+
+}  // extern "C"
+

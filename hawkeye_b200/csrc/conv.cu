@@ -1,0 +1,718 @@
+// VGG-16 backbone convolutions (reference model/backbone/vgg.py:56-70: Conv2d 3x3 s1 p1 + bias, ReLU,
+// MaxPool2d 2x2) as im2col-free implicit GEMMs on tcgen05 (kind::tf32, fp32 accumulate in TMEM).
+//
+// Layout: activations are NHWC fp32 inside the backbone.  For a 3x3 tap (kh,kw) the A operand of the
+// implicit GEMM is the input window shifted by (kh-1,kw-1); a 4-D TMA box {32 ch, TW, TH, TN} at the
+// shifted (possibly negative) coordinate lands as 128 rows x 128 B in 128B-swizzled shared memory —
+// exactly the K-major UMMA layout — and TMA's out-of-bounds zero fill *is* the conv padding.
+//   fwd   : Y[pix, co]  = sum_{tap,ci} X[pix+tap, ci] * Wf[tap][co][ci]        (+bias, ReLU)
+//   dgrad : dX[pix, ci] = sum_{tap,co} dY[pix+tap, co] * Wd[tap][ci][co]       (Wd = flipped/transposed W; * (act>0))
+//   wgrad : dW[tap][co][ci] = sum_pix dY[pix, co] * X[pix+tap, ci]             (both operands MN-major; split-K)
+#include "common.cuh"
+#include "host.h"
+#include "../../include/hawkeye_b200.h"
+
+namespace hk {
+
+// ------------------------------------------------------------------------------------------------
+// weight packing:  W [Cout][Cin][3][3]  ->  Wf [9][Cout][Cin]  and  Wd [9][Cin][Cout] (taps flipped)
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ W, float* __restrict__ Wf, float* __restrict__ Wd,
+                                    int Cout, int Cin) {
+  const size_t n = (size_t)Cout * Cin * 9;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int t = i % 9;
+    const int ci = (i / 9) % Cin;
+    const int co = i / ((size_t)9 * Cin);
+    const float v = tf32_round(W[i]);
+    if (Wf) Wf[((size_t)t * Cout + co) * Cin + ci] = v;
+    if (Wd) Wd[((size_t)(8 - t) * Cin + ci) * Cout + co] = v;
+  }
+}
+// dWp [9][Cout][Cin] -> dW [Cout][Cin][3][3]
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dWp, float* __restrict__ dW, int Cout, int Cin) {
+  const size_t n = (size_t)Cout * Cin * 9;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int t = i % 9;
+    const int ci = (i / 9) % Cin;
+    const int co = i / ((size_t)9 * Cin);
+    dW[i] = dWp[((size_t)t * Cout + co) * Cin + ci];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// implicit-GEMM conv (forward and data-gradient)
+// ------------------------------------------------------------------------------------------------
+struct ConvArgs {
+  float* Y;            // [N,H,W,Cout]
+  const float* bias;   // [Cout] or null
+  const float* mask;   // [N,H,W,Cout] or null: out *= (mask > 0)   (ReLU backward fused into dgrad)
+  int N, H, W, Cin, Cout;
+  int TW, TH, TN;      // pixel tile (product 128)
+  int tiles_w, tiles_h, tiles_n;
+  int relu;
+};
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int MIN_CTAS = (BN == 256) ? 1 : 2;
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, ConvCfg<BN>::MIN_CTAS)
+conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvArgs a) {
+  using Cfg = ConvCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + Cfg::STAGES;
+  uint64_t* accf = empty + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int t = blockIdx.x;
+  const int tw = t % a.tiles_w; t /= a.tiles_w;
+  const int th = t % a.tiles_h; t /= a.tiles_h;
+  const int w0 = tw * a.TW, h0 = th * a.TH, n0 = t * a.TN;
+  const int co0 = blockIdx.y * BN;
+  const int nchunk = a.Cin / 32;
+  const int nk = 9 * nchunk;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accf, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        const int tap = kb / nchunk, ck = kb - tap * nchunk;
+        const int kh = tap / 3, kw = tap - kh * 3;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        tma_load_4d(sA + s * Cfg::A_BYTES, &tmX, &full[s], ck * 32, w0 + kw - 1, h0 + kh - 1, n0);
+        tma_load_3d(sB + s * Cfg::B_BYTES, &tmW, &full[s], ck * 32, co0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
+        const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_tf32_ss(tmem_base, make_sdesc(a_addr + ks * 32, 16, 1024), make_sdesc(b_addr + ks * 32, 16, 1024), idesc,
+                       (kb | ks) ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accf);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int wi = r % a.TW, hi = (r / a.TW) % a.TH, ni = r / (a.TW * a.TH);
+    const int w = w0 + wi, h = h0 + hi, n = n0 + ni;
+    const bool valid = (w < a.W) && (h < a.H) && (n < a.N);
+    const size_t pix = ((size_t)n * a.H + h) * a.W + w;
+    mbar_wait(accf, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      const int co = co0 + c * 32;
+      if (valid && co < a.Cout) {
+        if (a.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + co + j);
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (a.mask) {
+          const float4* m = reinterpret_cast<const float4*>(a.mask + pix * a.Cout + co);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 mm = m[j];
+            v[4 * j] = mm.x > 0.f ? v[4 * j] : 0.f;
+            v[4 * j + 1] = mm.y > 0.f ? v[4 * j + 1] : 0.f;
+            v[4 * j + 2] = mm.z > 0.f ? v[4 * j + 2] : 0.f;
+            v[4 * j + 3] = mm.w > 0.f ? v[4 * j + 3] : 0.f;
+          }
+        }
+        float4* dst = reinterpret_cast<float4*>(a.Y + pix * a.Cout + co);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(tf32_round(v[4 * j]), tf32_round(v[4 * j + 1]), tf32_round(v[4 * j + 2]),
+                               tf32_round(v[4 * j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// pick a pixel tile TW x TH x TN with product `target` that tiles W x H (x N) with as little waste as possible
+static void pick_tile(int W, int H, int N, int target, int* TW, int* TH, int* TN) {
+  int tw = 1;
+  while (tw * 2 <= 16 && W % (tw * 2) == 0 && tw * 2 <= target) tw *= 2;
+  int th = 1;
+  while (th * 2 * tw <= target && H % (th * 2) == 0) th *= 2;
+  int tn = target / (tw * th);
+  // if the map is tiny (e.g. 2x2) the remainder goes to the batch dimension
+  *TW = tw; *TH = th; *TN = tn;
+  (void)N;
+}
+
+static int make_act_map(CUtensorMap* tm, const float* X, int N, int H, int W, int C, int TW, int TH, int TN) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+  uint32_t box[4] = {32, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
+  return make_tmap(tm, X, 4, dims, strides, box);
+}
+
+template <int BN>
+static int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvArgs& a, cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(conv<%d>): %s", BN, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid(a.tiles_w * a.tiles_h * a.tiles_n, (a.Cout + BN - 1) / BN);
+  conv3x3_igemm_kernel<BN><<<grid, 192, Cfg::SMEM, stream>>>(tmX, tmW, a);
+  HK_LAUNCH_CHECK("conv3x3_igemm_kernel");
+  return 0;
+}
+
+// x NHWC [N,H,W,Cin], wp packed [9][Cout][Cin] -> y NHWC [N,H,W,Cout]
+int conv3x3_igemm(const float* x, const float* wp, const float* bias, const float* mask, float* y, int N, int H, int W,
+                  int Cin, int Cout, int relu, cudaStream_t stream) {
+  HK_REQUIRE(x && wp && y, HK_ERR_ARG, "conv3x3: null pointer");
+  HK_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0, HK_ERR_UNSUPPORTED, "conv3x3: Cin=%d Cout=%d must be multiples of 32",
+             Cin, Cout);
+  HK_REQUIRE(aligned16(x) && aligned16(wp) && aligned16(y) && (!mask || aligned16(mask)), HK_ERR_ALIGN,
+             "conv3x3: pointer not 16-byte aligned");
+  ConvArgs a = {};
+  a.Y = y; a.bias = bias; a.mask = mask; a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.relu = relu;
+  pick_tile(W, H, N, 128, &a.TW, &a.TH, &a.TN);
+  a.tiles_w = (W + a.TW - 1) / a.TW; a.tiles_h = (H + a.TH - 1) / a.TH; a.tiles_n = (N + a.TN - 1) / a.TN;
+  HK_REQUIRE((long long)a.tiles_w * a.tiles_h * a.tiles_n < (1ll << 31), HK_ERR_UNSUPPORTED, "conv3x3: grid too large");
+  CUtensorMap tmX, tmW;
+  int r;
+  if ((r = make_act_map(&tmX, x, N, H, W, Cin, a.TW, a.TH, a.TN))) return r;
+  const int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+  {
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
+    uint64_t strides[2] = {(uint64_t)Cin * 4, (uint64_t)Cin * Cout * 4};
+    uint32_t box[3] = {32, (uint32_t)BN, 1};
+    if ((r = make_tmap(&tmW, wp, 3, dims, strides, box))) return r;
+  }
+  if (BN == 64) return launch_conv<64>(tmX, tmW, a, stream);
+  if (BN == 128) return launch_conv<128>(tmX, tmW, a, stream);
+  return launch_conv<256>(tmX, tmW, a, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: dWp[tap][co][ci] += sum over this CTA's pixel tiles of dY[pix,co] * X[pix+tap,ci]
+// A = dY (M = co, MN-major), B = X shifted (N = ci, MN-major); 64 pixels (k) per pipeline stage.
+// ------------------------------------------------------------------------------------------------
+struct WgradArgs {
+  float* dWp;  // [9][Cout][Cin], pre-zeroed; accumulated with fp32 atomics (split-K over pixel tiles)
+  int N, H, W, Cin, Cout;
+  int TW, TH, TN, tiles_w, tiles_h, tiles_n;
+  int ksplit;
+};
+
+template <int BN>
+struct WgradCfg {
+  static constexpr int KP = 64;
+  static constexpr int STAGES = (BN == 128) ? 3 : 4;
+  static constexpr int A_BYTES = 4 * KP * 128;          // 4 co-blocks of [KP x 128 B]
+  static constexpr int B_BYTES = (BN / 32) * KP * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, WgradArgs a) {
+  using Cfg = WgradCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + Cfg::STAGES;
+  uint64_t* accf = empty + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_ci_tiles = a.Cin / BN;
+  int t = blockIdx.x;
+  const int ci_t = t % n_ci_tiles; t /= n_ci_tiles;
+  const int co_t = t;
+  const int tap = blockIdx.y;
+  const int kh = tap / 3, kw = tap - kh * 3;
+  const int split = blockIdx.z;
+  const int co0 = co_t * 128, ci0 = ci_t * BN;
+  const long long total_tiles = (long long)a.tiles_w * a.tiles_h * a.tiles_n;
+  const long long per = (total_tiles + a.ksplit - 1) / a.ksplit;
+  const long long t_begin = per * split;
+  const long long t_end = (t_begin + per < total_tiles) ? t_begin + per : total_tiles;
+  const int nk = (int)(t_end > t_begin ? t_end - t_begin : 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accf, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nk > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int kb = 0; kb < nk; ++kb) {
+          const int s = kb % Cfg::STAGES;
+          const uint32_t ph = (kb / Cfg::STAGES) & 1;
+          long long tt = t_begin + kb;
+          const int tw = tt % a.tiles_w; tt /= a.tiles_w;
+          const int th = tt % a.tiles_h; tt /= a.tiles_h;
+          const int w0 = tw * a.TW, h0 = th * a.TH, n0 = (int)tt * a.TN;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          uint8_t* pa = sA + s * Cfg::A_BYTES;
+          uint8_t* pb = sB + s * Cfg::B_BYTES;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_4d(pa + j * Cfg::KP * 128, &tmDY, &full[s], co0 + j * 32, w0, h0, n0);
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j)
+            tma_load_4d(pb + j * Cfg::KP * 128, &tmX, &full[s], ci0 + j * 32, w0 + kw - 1, h0 + kh - 1, n0);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_tf32(128, BN, 1, 1);
+        for (int kb = 0; kb < nk; ++kb) {
+          const int s = kb % Cfg::STAGES;
+          const uint32_t ph = (kb / Cfg::STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < Cfg::KP / 8; ++ks)
+            umma_tf32_ss(tmem_base, make_sdesc(a_addr + ks * 1024, Cfg::KP * 128, 1024),
+                         make_sdesc(b_addr + ks * 1024, Cfg::KP * 128, 1024), idesc, (kb | ks) ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(accf);
+      }
+    } else {
+      const int q = warp & 3;
+      const int co = co0 + q * 32 + lane;
+      mbar_wait(accf, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+        tmem_ld_wait();
+        if (co < a.Cout) {
+          float* dst = a.dWp + ((size_t)tap * a.Cout + co) * a.Cin + ci0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradArgs& a, cudaStream_t stream) {
+  using Cfg = WgradCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(wgrad<%d>): %s", BN, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid(((a.Cout + 127) / 128) * (a.Cin / BN), 9, a.ksplit);
+  conv3x3_wgrad_kernel<BN><<<grid, 192, Cfg::SMEM, stream>>>(tmDY, tmX, a);
+  HK_LAUNCH_CHECK("conv3x3_wgrad_kernel");
+  return 0;
+}
+
+int conv3x3_wgrad(const float* x, const float* dy, float* dwp, int N, int H, int W, int Cin, int Cout,
+                  cudaStream_t stream) {
+  HK_REQUIRE(x && dy && dwp, HK_ERR_ARG, "conv3x3_wgrad: null pointer");
+  HK_REQUIRE(Cin % 64 == 0 && Cout % 32 == 0, HK_ERR_UNSUPPORTED, "conv3x3_wgrad: Cin=%d Cout=%d unsupported", Cin, Cout);
+  WgradArgs a = {};
+  a.dWp = dwp; a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
+  pick_tile(W, H, N, 64, &a.TW, &a.TH, &a.TN);
+  a.tiles_w = (W + a.TW - 1) / a.TW; a.tiles_h = (H + a.TH - 1) / a.TH; a.tiles_n = (N + a.TN - 1) / a.TN;
+  const int BN = (Cin % 128 == 0) ? 128 : 64;
+  const long long out_tiles = (long long)((Cout + 127) / 128) * (Cin / BN) * 9;
+  const long long total_tiles = (long long)a.tiles_w * a.tiles_h * a.tiles_n;
+  long long ks = (148 * 2 + out_tiles - 1) / out_tiles;
+  if (ks > total_tiles) ks = total_tiles;
+  if (ks < 1) ks = 1;
+  if (ks > 65535) ks = 65535;
+  a.ksplit = (int)ks;
+  CUtensorMap tmDY, tmX;
+  int r;
+  if ((r = make_act_map(&tmDY, dy, N, H, W, Cout, a.TW, a.TH, a.TN))) return r;
+  if ((r = make_act_map(&tmX, x, N, H, W, Cin, a.TW, a.TH, a.TN))) return r;
+  cudaError_t e = cudaMemsetAsync(dwp, 0, (size_t)9 * Cout * Cin * sizeof(float), stream);
+  if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(dWp): %s", cudaGetErrorString(e));
+  if (BN == 128) return launch_wgrad<128>(tmDY, tmX, a, stream);
+  return launch_wgrad<64>(tmDY, tmX, a, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// first layer (Cin = 3): direct fp32 conv, NCHW image in -> NHWC out, + bias + ReLU   (vgg.py:61, in_channels=3)
+// ------------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ y,
+                                                            int N, int H, int W) {
+  __shared__ float sw[COUT * 27];
+  __shared__ float sb[COUT];
+  for (int i = threadIdx.x; i < COUT * 27; i += blockDim.x) {
+    // w [COUT][3][3][3] (co, ci, kh, kw) -> sw[(ci*9+kh*3+kw)*COUT + co]
+    const int co = i / 27, r = i % 27;
+    sw[r * COUT + co] = w[i];
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  // each thread: one pixel, 16 output channels (COUT/16 thread-groups share a pixel)
+  constexpr int G = COUT / 16;
+  const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long pix = gid / G;
+  const int g = (int)(gid % G);
+  const long long total = (long long)N * H * W;
+  if (pix >= total) return;
+  const int wq = (int)(pix % W);
+  const int hq = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  float in[27];
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int hh = hq + kh - 1, ww = wq + kw - 1;
+        in[ci * 9 + kh * 3 + kw] =
+            (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(x + (((size_t)n * 3 + ci) * H + hh) * W + ww) : 0.f;
+      }
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = sb[g * 16 + j];
+#pragma unroll
+  for (int r = 0; r < 27; ++r) {
+    const float xv = in[r];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = fmaf(xv, sw[r * COUT + g * 16 + j], acc[j]);
+  }
+  float4* dst = reinterpret_cast<float4*>(y + (size_t)pix * COUT + g * 16);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    dst[j] = make_float4(tf32_round(fmaxf(acc[4 * j], 0.f)), tf32_round(fmaxf(acc[4 * j + 1], 0.f)),
+                         tf32_round(fmaxf(acc[4 * j + 2], 0.f)), tf32_round(fmaxf(acc[4 * j + 3], 0.f)));
+}
+
+// first-layer weight gradient: dW[co][ci][kh][kw] = sum_pix dY[pix][co] * x[n][ci][h+kh-1][w+kw-1]; dY NHWC (already
+// ReLU-masked).  Block = 128 pixels x COUT; per-block partial sums reduced through shared memory, then atomics.
+template <int COUT>
+__global__ void __launch_bounds__(256) conv3x3_first_wgrad_kernel(const float* __restrict__ x,
+                                                                  const float* __restrict__ dy, float* __restrict__ dw,
+                                                                  int N, int H, int W, int pix_per_block) {
+  __shared__ float sx[64][28];      // 64 pixels x 27 taps (+pad)
+  __shared__ float sdy[64][COUT + 1];
+  const long long total = (long long)N * H * W;
+  const long long p_begin = (long long)blockIdx.x * pix_per_block;
+  const long long p_end = (p_begin + pix_per_block < total) ? p_begin + pix_per_block : total;
+  // thread -> (r, co-group): 27 taps x COUT outputs = 27*COUT accumulators over 256 threads
+  constexpr int PER = (27 * COUT + 255) / 256;
+  float acc[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) acc[i] = 0.f;
+  for (long long p0 = p_begin; p0 < p_end; p0 += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 27; i += 256) {
+      const int pp = i / 27, r = i % 27;
+      const long long pix = p0 + pp;
+      float v = 0.f;
+      if (pix < p_end) {
+        const int wq = (int)(pix % W), hq = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+        const int ci = r / 9, kh = (r % 9) / 3, kw = r % 3;
+        const int hh = hq + kh - 1, ww = wq + kw - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + (((size_t)n * 3 + ci) * H + hh) * W + ww);
+      }
+      sx[pp][r] = v;
+    }
+    for (int i = threadIdx.x; i < 64 * COUT; i += 256) {
+      const int pp = i / COUT, co = i % COUT;
+      const long long pix = p0 + pp;
+      sdy[pp][co] = (pix < p_end) ? dy[(size_t)pix * COUT + co] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      if (idx < 27 * COUT) {
+        const int co = idx % COUT, r = idx / COUT;
+        float s = 0.f;
+#pragma unroll 16
+        for (int pp = 0; pp < 64; ++pp) s = fmaf(sdy[pp][co], sx[pp][r], s);
+        acc[i] += s;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int idx = threadIdx.x + i * 256;
+    if (idx < 27 * COUT) {
+      const int co = idx % COUT, r = idx / COUT;
+      atomicAdd(dw + (size_t)co * 27 + r, acc[i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPool2d(2,2) (vgg.py:59) on NHWC; optional NCHW output for the last pool (feeds the pooling head)
+// ------------------------------------------------------------------------------------------------
+__global__ void maxpool2x2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C,
+                                      int out_nchw) {
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const size_t total = (size_t)N * Ho * Wo * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = i % C4;
+    size_t p = i / C4;
+    const int wo = p % Wo; p /= Wo;
+    const int ho = p % Ho;
+    const int n = p / Ho;
+    const float4* base = reinterpret_cast<const float4*>(x + (((size_t)n * H + 2 * ho) * W + 2 * wo) * C) + c4;
+    const float4 a = base[0], b = base[C4], c = base[(size_t)W * C4], d = base[(size_t)W * C4 + C4];
+    float4 m;
+    m.x = fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x));
+    m.y = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
+    m.z = fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z));
+    m.w = fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w));
+    if (!out_nchw) {
+      reinterpret_cast<float4*>(y + (((size_t)n * Ho + ho) * Wo + wo) * C)[c4] = m;
+    } else {
+      const size_t hw = (size_t)Ho * Wo, o = ((size_t)n * C + c4 * 4) * hw + (size_t)ho * Wo + wo;
+      y[o] = m.x; y[o + hw] = m.y; y[o + 2 * hw] = m.z; y[o + 3 * hw] = m.w;
+    }
+  }
+}
+
+// backward: dx[window] = dy routed to the first max in scan order (PyTorch max_pool2d_backward), then multiplied by
+// (x > 0): x is the ReLU output feeding the pool, so this also applies the preceding ReLU's backward.
+__global__ void maxpool2x2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                      float* __restrict__ dx, int N, int H, int W, int C, int dy_nchw) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)N * Ho * Wo * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    size_t p = i / C;
+    const int wo = p % Wo; p /= Wo;
+    const int ho = p % Ho;
+    const int n = p / Ho;
+    const size_t b00 = (((size_t)n * H + 2 * ho) * W + 2 * wo) * C + c;
+    const size_t b01 = b00 + C, b10 = b00 + (size_t)W * C, b11 = b10 + C;
+    const float v00 = x[b00], v01 = x[b01], v10 = x[b10], v11 = x[b11];
+    const float g = dy_nchw ? dy[((size_t)n * C + c) * Ho * Wo + (size_t)ho * Wo + wo] : dy[i];
+    int arg = 0;
+    float m = v00;
+    if (v01 > m) { m = v01; arg = 1; }
+    if (v10 > m) { m = v10; arg = 2; }
+    if (v11 > m) { m = v11; arg = 3; }
+    const float gm = m > 0.f ? g : 0.f;
+    dx[b00] = arg == 0 ? gm : 0.f;
+    dx[b01] = arg == 1 ? gm : 0.f;
+    dx[b10] = arg == 2 ? gm : 0.f;
+    dx[b11] = arg == 3 ? gm : 0.f;
+  }
+}
+
+// db[c] = sum over pixels of dy[pix][c]   (NHWC)
+__global__ void bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, size_t npix, int C) {
+  // block handles a slab of pixels; threads stride over channels (coalesced), atomics at the end
+  const int c = threadIdx.x % C;
+  const int lanes_per_c = blockDim.x / C > 0 ? blockDim.x / C : 1;
+  const int sub = threadIdx.x / C;
+  if (sub >= lanes_per_c) return;
+  const size_t per = (npix + gridDim.x - 1) / gridDim.x;
+  const size_t p0 = blockIdx.x * per, p1 = (p0 + per < npix) ? p0 + per : npix;
+  for (int cc = c; cc < C; cc += (blockDim.x < C ? blockDim.x : C)) {
+    float s = 0.f;
+    for (size_t p = p0 + sub; p < p1; p += lanes_per_c) s += dy[p * C + cc];
+    atomicAdd(db + cc, s);
+  }
+}
+
+// elementwise: dy *= (act > 0)
+__global__ void relu_mask_kernel(float* __restrict__ dy, const float* __restrict__ act, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 g = reinterpret_cast<float4*>(dy)[i];
+    const float4 a = reinterpret_cast<const float4*>(act)[i];
+    g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f; g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
+    reinterpret_cast<float4*>(dy)[i] = g;
+  }
+}
+
+static inline int grid_for(size_t n, int block) {
+  size_t g = (n + block - 1) / block;
+  const size_t cap = 148 * 16;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace hk
+
+using namespace hk;
+
+extern "C" {
+
+int hk_conv3x3_pack_weights(const float* w, float* w_fwd, float* w_dgrad, int Cout, int Cin, void* stream) {
+  HK_REQUIRE(w && (w_fwd || w_dgrad), HK_ERR_ARG, "hk_conv3x3_pack_weights: null pointer");
+  pack_weights_kernel<<<grid_for((size_t)Cout * Cin * 9, 256), 256, 0, (cudaStream_t)stream>>>(w, w_fwd, w_dgrad, Cout, Cin);
+  HK_LAUNCH_CHECK("pack_weights_kernel");
+  return 0;
+}
+
+int hk_conv3x3_fwd(const float* x, const float* w_packed, const float* bias, float* y, int N, int H, int W, int Cin,
+                   int Cout, int relu, void* stream) {
+  return conv3x3_igemm(x, w_packed, bias, nullptr, y, N, H, W, Cin, Cout, relu, (cudaStream_t)stream);
+}
+
+int hk_conv3x3_dgrad(const float* dy, const float* w_dgrad_packed, const float* relu_mask_act, float* dx, int N, int H,
+                     int W, int Cin, int Cout, void* stream) {
+  // dgrad is the same implicit GEMM with the roles of Cin/Cout swapped and flipped taps
+  return conv3x3_igemm(dy, w_dgrad_packed, nullptr, relu_mask_act, dx, N, H, W, Cout, Cin, 0, (cudaStream_t)stream);
+}
+
+size_t hk_conv3x3_wgrad_workspace_bytes(int Cin, int Cout) { return (size_t)9 * Cin * Cout * sizeof(float); }
+
+int hk_conv3x3_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int H, int W, int Cin, int Cout,
+                     void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  HK_REQUIRE(workspace && workspace_bytes >= hk_conv3x3_wgrad_workspace_bytes(Cin, Cout), HK_ERR_WORKSPACE,
+             "hk_conv3x3_wgrad: workspace too small");
+  float* dwp = static_cast<float*>(workspace);
+  int r = conv3x3_wgrad(x, dy, dwp, N, H, W, Cin, Cout, stream);
+  if (r) return r;
+  unpack_wgrad_kernel<<<grid_for((size_t)Cout * Cin * 9, 256), 256, 0, stream>>>(dwp, dw, Cout, Cin);
+  HK_LAUNCH_CHECK("unpack_wgrad_kernel");
+  if (db) {
+    cudaError_t e = cudaMemsetAsync(db, 0, Cout * sizeof(float), stream);
+    if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(db): %s", cudaGetErrorString(e));
+    const size_t npix = (size_t)N * H * W;
+    const int block = Cout >= 256 ? Cout : 256;
+    bias_grad_kernel<<<grid_for(npix, 64), block, 0, stream>>>(dy, db, npix, Cout);
+    HK_LAUNCH_CHECK("bias_grad_kernel");
+  }
+  return 0;
+}
+
+int hk_conv3x3_first_fwd(const float* x_nchw, const float* w, const float* bias, float* y_nhwc, int N, int H, int W,
+                         int Cout, void* stream) {
+  HK_REQUIRE(x_nchw && w && y_nhwc, HK_ERR_ARG, "hk_conv3x3_first_fwd: null pointer");
+  HK_REQUIRE(Cout == 64 || Cout == 32 || Cout == 16, HK_ERR_UNSUPPORTED, "hk_conv3x3_first_fwd: Cout=%d unsupported", Cout);
+  const long long threads = (long long)N * H * W * (Cout / 16);
+  const int grid = (int)((threads + 255) / 256);
+  if (Cout == 64) conv3x3_first_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, w, bias, y_nhwc, N, H, W);
+  else if (Cout == 32) conv3x3_first_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, w, bias, y_nhwc, N, H, W);
+  else conv3x3_first_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, w, bias, y_nhwc, N, H, W);
+  HK_LAUNCH_CHECK("conv3x3_first_kernel");
+  return 0;
+}
+
+int hk_conv3x3_first_wgrad(const float* x_nchw, const float* dy_nhwc, float* dw, float* db, int N, int H, int W,
+                           int Cout, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  HK_REQUIRE(x_nchw && dy_nhwc && dw, HK_ERR_ARG, "hk_conv3x3_first_wgrad: null pointer");
+  HK_REQUIRE(Cout == 64 || Cout == 32 || Cout == 16, HK_ERR_UNSUPPORTED, "hk_conv3x3_first_wgrad: Cout=%d unsupported", Cout);
+  cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)Cout * 27 * sizeof(float), stream);
+  if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(dw): %s", cudaGetErrorString(e));
+  const long long total = (long long)N * H * W;
+  long long ppb = (total + 148 * 8 - 1) / (148 * 8);
+  ppb = ((ppb + 63) / 64) * 64;
+  const int grid = (int)((total + ppb - 1) / ppb);
+  if (Cout == 64) conv3x3_first_wgrad_kernel<64><<<grid, 256, 0, stream>>>(x_nchw, dy_nhwc, dw, N, H, W, (int)ppb);
+  else if (Cout == 32) conv3x3_first_wgrad_kernel<32><<<grid, 256, 0, stream>>>(x_nchw, dy_nhwc, dw, N, H, W, (int)ppb);
+  else conv3x3_first_wgrad_kernel<16><<<grid, 256, 0, stream>>>(x_nchw, dy_nhwc, dw, N, H, W, (int)ppb);
+  HK_LAUNCH_CHECK("conv3x3_first_wgrad_kernel");
+  if (db) {
+    e = cudaMemsetAsync(db, 0, Cout * sizeof(float), stream);
+    if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(db): %s", cudaGetErrorString(e));
+    bias_grad_kernel<<<grid_for((size_t)total, 64), 256, 0, stream>>>(dy_nhwc, db, (size_t)total, Cout);
+    HK_LAUNCH_CHECK("bias_grad_kernel");
+  }
+  return 0;
+}
+
+int hk_maxpool2x2_fwd(const float* x_nhwc, float* y, int N, int H, int W, int C, int out_nchw, void* stream) {
+  HK_REQUIRE(x_nhwc && y, HK_ERR_ARG, "hk_maxpool2x2_fwd: null pointer");
+  HK_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, HK_ERR_UNSUPPORTED, "hk_maxpool2x2_fwd: C%%4, even H/W required");
+  const size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 4);
+  maxpool2x2_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x_nhwc, y, N, H, W, C, out_nchw);
+  HK_LAUNCH_CHECK("maxpool2x2_fwd_kernel");
+  return 0;
+}
+
+int hk_maxpool2x2_bwd(const float* x_nhwc, const float* dy, float* dx_nhwc, int N, int H, int W, int C, int dy_nchw,
+                      void* stream) {
+  HK_REQUIRE(x_nhwc && dy && dx_nhwc, HK_ERR_ARG, "hk_maxpool2x2_bwd: null pointer");
+  HK_REQUIRE(H % 2 == 0 && W % 2 == 0, HK_ERR_UNSUPPORTED, "hk_maxpool2x2_bwd: even H/W required");
+  const size_t total = (size_t)N * (H / 2) * (W / 2) * C;
+  maxpool2x2_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x_nhwc, dy, dx_nhwc, N, H, W, C, dy_nchw);
+  HK_LAUNCH_CHECK("maxpool2x2_bwd_kernel");
+  return 0;
+}
+
+int hk_relu_mask_inplace(float* dy, const float* act, size_t n, void* stream) {
+  HK_REQUIRE(dy && act && n % 4 == 0, HK_ERR_ARG, "hk_relu_mask_inplace: bad args");
+  relu_mask_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(dy, act, n / 4);
+  HK_LAUNCH_CHECK("relu_mask_kernel");
+  return 0;
+}
+
+}  // extern "C"

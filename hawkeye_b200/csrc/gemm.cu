@@ -1,0 +1,234 @@
+// Generic batched TF32 GEMM on tcgen05 (UMMA) with TMA-fed, 128B-swizzled shared-memory
+// operands and the fp32 accumulator in TMEM.  One 128 x BN output tile per CTA.
+//
+//   C[b] = alpha_b * (A[b] . B[b]) + diag * I + beta_b * D[b]           (optionally stored transposed)
+//
+// Both operands may be K-major or MN-major in global memory, so the same kernel serves
+//   * Newton-Schulz chains and covariance of Fast MPN-COV (reference model/methods/MPNCOV.py:105-202),
+//   * the (S . X) contraction of the bilinear / compact-bilinear backward (BCNN.py:13-27, CBCNN.py:96-135),
+//   * 1x1 convolutions in NHWC (model/backbone/resnet.py:29-37).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue.
+#include "common.cuh"
+#include "host.h"
+#include "../../include/hawkeye_b200.h"
+
+namespace hk {
+
+struct GemmEpi {
+  float* C;
+  long long ldc, strideC;
+  const float* D;
+  long long ldd, strideD;
+  const float* alpha_vec;
+  const float* beta_vec;
+  float alpha, beta, diag;
+  int trans_c;
+  int relu;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpi epi, int M,
+                 int N, int K, int a_mn, int b_mn, int shareA, int shareB) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + Cfg::STAGES;
+  uint64_t* accf = empty + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN, bz = blockIdx.z;
+  const int nk = (K + 31) / 32;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accf, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int bza = shareA ? 0 : bz, bzb = shareB ? 0 : bz;
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        uint8_t* a = sA + s * Cfg::A_BYTES;
+        uint8_t* b = sB + s * Cfg::B_BYTES;
+        if (!a_mn) {
+          tma_load_3d(a, &tmA, &full[s], kb * 32, m0, bza);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_3d(a + j * 4096, &tmA, &full[s], m0 + j * 32, kb * 32, bza);
+        }
+        if (!b_mn) {
+          tma_load_3d(b, &tmB, &full[s], kb * 32, n0, bzb);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_3d(b + j * 4096, &tmB, &full[s], n0 + j * 32, kb * 32, bzb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, BN, a_mn, b_mn);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
+        const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+        const int krem = K - kb * 32;
+        const int ksteps = krem >= 32 ? 4 : (krem + 7) / 8;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t ad = a_mn ? make_sdesc(a_addr + ks * 1024, 4096, 1024) : make_sdesc(a_addr + ks * 32, 16, 1024);
+          const uint64_t bd = b_mn ? make_sdesc(b_addr + ks * 1024, 4096, 1024) : make_sdesc(b_addr + ks * 32, 16, 1024);
+          umma_tf32_ss(tmem_base, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accf);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(accf, 0);
+    tc_fence_after();
+    const float alpha = epi.alpha * (epi.alpha_vec ? epi.alpha_vec[bz] : 1.f);
+    const float beta = epi.beta * (epi.beta_vec ? epi.beta_vec[bz] : 1.f);
+    float* Cb = epi.C + (long long)bz * epi.strideC;
+    const float* Db = epi.D ? epi.D + (long long)bz * epi.strideD : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      const int col0 = n0 + c * 32;
+      if (row < M && col0 < N) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          float o = alpha * v[j];
+          if (col == row) o += epi.diag;
+          if (Db && col < N) o += beta * Db[(long long)row * epi.ldd + col];
+          if (epi.relu) o = fmaxf(o, 0.f);
+          v[j] = o;
+        }
+        if (!epi.trans_c) {
+          float* dst = Cb + (long long)row * epi.ldc + col0;
+          if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) dst[j] = v[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) Cb[(long long)(col0 + j) * epi.ldc + row] = v[j];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+static int make_operand_map(CUtensorMap* tm, const float* P, int mn_major, long long ld, long long stride, int rows,
+                            int K, int batch, int tile_rows, int* share) {
+  *share = (stride == 0 || batch == 1);
+  uint64_t dims[3], strides[2];
+  uint32_t box[3];
+  const uint64_t nb = *share ? 1 : (uint64_t)batch;
+  const uint64_t bs = *share ? (uint64_t)(mn_major ? K : rows) * ld * 4 : (uint64_t)stride * 4;
+  if (!mn_major) {  // [rows][K], K contiguous
+    dims[0] = K; dims[1] = rows; dims[2] = nb;
+    box[0] = 32; box[1] = tile_rows; box[2] = 1;
+  } else {          // [K][rows], rows contiguous
+    dims[0] = rows; dims[1] = K; dims[2] = nb;
+    box[0] = 32; box[1] = 32; box[2] = 1;
+  }
+  strides[0] = (uint64_t)ld * 4;
+  strides[1] = bs;
+  return make_tmap(tm, P, 3, dims, strides, box);
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi& epi, int M, int N, int K,
+                       int batch, int a_mn, int b_mn, int shareA, int shareB, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(gemm<%d>): %s", BN, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((M + 127) / 128, (N + BN - 1) / BN, batch);
+  umma_gemm_kernel<BN><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, epi, M, N, K, a_mn, b_mn, shareA, shareB);
+  HK_LAUNCH_CHECK("umma_gemm_kernel");
+  return 0;
+}
+
+int gemm_tf32(const float* A, int a_mn, long long lda, long long strideA, const float* B, int b_mn, long long ldb,
+              long long strideB, const GemmEpi& epi, int M, int N, int K, int batch, cudaStream_t stream) {
+  HK_REQUIRE(A && B && epi.C, HK_ERR_ARG, "gemm: null pointer");
+  HK_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, HK_ERR_ARG, "gemm: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
+  HK_REQUIRE(batch <= 65535, HK_ERR_UNSUPPORTED, "gemm: batch %d > 65535", batch);
+  CUtensorMap tmA, tmB;
+  int shareA, shareB, r;
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  if ((r = make_operand_map(&tmA, A, a_mn, lda, strideA, M, K, batch, 128, &shareA))) return r;
+  if ((r = make_operand_map(&tmB, B, b_mn, ldb, strideB, N, K, batch, BN, &shareB))) return r;
+  if (BN == 64) return launch_gemm<64>(tmA, tmB, epi, M, N, K, batch, a_mn, b_mn, shareA, shareB, stream);
+  if (BN == 128) return launch_gemm<128>(tmA, tmB, epi, M, N, K, batch, a_mn, b_mn, shareA, shareB, stream);
+  return launch_gemm<256>(tmA, tmB, epi, M, N, K, batch, a_mn, b_mn, shareA, shareB, stream);
+}
+
+}  // namespace hk
+
+extern "C" int hk_gemm_tf32(const float* A, int a_mn_major, long long lda, long long strideA, const float* B,
+                            int b_mn_major, long long ldb, long long strideB, float* C, long long ldc,
+                            long long strideC, int trans_c, int M, int N, int K, int batch, float alpha,
+                            const float* alpha_vec, float diag, const float* D, long long ldd, long long strideD,
+                            float beta, const float* beta_vec, int relu, void* stream) {
+  hk::GemmEpi epi;
+  epi.C = C; epi.ldc = ldc; epi.strideC = strideC;
+  epi.D = D; epi.ldd = ldd; epi.strideD = strideD;
+  epi.alpha_vec = alpha_vec; epi.beta_vec = beta_vec;
+  epi.alpha = alpha; epi.beta = beta; epi.diag = diag;
+  epi.trans_c = trans_c; epi.relu = relu;
+  return hk::gemm_tf32(A, a_mn_major, lda, strideA, B, b_mn_major, ldb, strideB, epi, M, N, K, batch,
+                       static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,44 @@
+// Host-side helpers shared by the C-ABI translation units: error convention
+// (0 ok / <0 argument error, no launch / >0 cudaError_t), thread-local last-error text,
+// and CUtensorMap construction through the driver entry point (no libcuda link dependency).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define HK_OK 0
+#define HK_ERR_ARG (-1)
+#define HK_ERR_ALIGN (-2)
+#define HK_ERR_UNSUPPORTED (-3)
+#define HK_ERR_WORKSPACE (-4)
+#define HK_ERR_DRIVER (-5)
+
+namespace hk {
+
+char* last_error_buf();
+int set_error(int code, const char* fmt, ...);
+int check_launch(const char* what);
+extern thread_local long long g_launches;  // kernels launched by this library on this thread
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Encode a tiled fp32 tensor map with SWIZZLE_128B and zero OOB fill.
+// dims/box are innermost-first; strides_bytes[i] is the byte stride of dim i+1 (rank-1 entries).
+int make_tmap(CUtensorMap* out, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, const uint32_t* elem_strides = nullptr);
+
+#define HK_REQUIRE(cond, code, ...) \
+  do {                              \
+    if (!(cond)) return hk::set_error(code, __VA_ARGS__); \
+  } while (0)
+
+#define HK_LAUNCH_CHECK(what)          \
+  do {                                 \
+    hk::g_launches++;                  \
+    int _e = hk::check_launch(what);   \
+    if (_e) return _e;                 \
+  } while (0)
+
+}  // namespace hk

@@ -1,0 +1,36 @@
+"""BCNN with the reference's constructor / attribute / state_dict surface (model/methods/BCNN.py:30-55)."""
+import torch.nn as nn
+
+from .. import ops
+from ..backbone.vgg import vgg16
+from ..registry import MODEL
+from ..utils import initialize_weights
+
+
+class BilinearPooling(nn.Module):
+    """Fused Gram + sqrt(.+1e-5) + L2-normalise (BCNN.py:8-27) on the tcgen05 kernel."""
+
+    def forward(self, x):
+        return ops.bilinear_pool(x)
+
+
+@MODEL.register
+class BCNN(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.stage = config.stage if 'stage' in config else 2          # BCNN.py:36
+        self.backbone = vgg16(pretrained=True)                           # BCNN.py:38-39 (all 31 feature layers)
+        self.bilinear_pooling = BilinearPooling()
+        self.classifier = nn.Linear(self.backbone.out_channels ** 2, config.num_classes)
+        self.classifier.apply(initialize_weights)
+        if self.stage == 1:                                              # BCNN.py:45-47
+            for p in self.backbone.parameters():
+                p.requires_grad = False
+        self.backbone.train_backbone = self.stage != 1
+
+    def forward(self, x):
+        x = self.backbone(x)
+        if self.stage == 1:
+            x = x.detach()
+        x = self.bilinear_pooling(x)
+        return ops.linear(x, self.classifier.weight, self.classifier.bias)

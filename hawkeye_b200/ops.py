@@ -1,0 +1,268 @@
+"""torch.autograd bindings of the C-ABI kernels (host plumbing only: memory, streams, autograd edges).
+
+Every op here calls ``libhawkeye_b200.so`` through ``_lib.call``; there is no PyTorch-eager fallback.
+PyTorch owns all device buffers (caching allocator) incl. workspaces and saved-for-backward tensors.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+VGG16_D = (64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M')
+
+
+def _check_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.HawkeyeLibError('hawkeye_b200 ops need CUDA tensors (there is no CPU fallback)')
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise _lib.HawkeyeLibError(f'hawkeye_b200 ops are fp32 (got {t.dtype})')
+    return t.contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# BCNN bilinear pooling (reference model/methods/BCNN.py:8-27)
+# ----------------------------------------------------------------------------------------------------------
+class BilinearPoolFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _check_cuda(x)
+        x = _f32c(x)
+        B, C, H, W = x.shape
+        hw = H * W
+        y = torch.empty(B, C * C, device=x.device, dtype=torch.float32)
+        ws = _ws(_lib.query('hk_bilinear_pool_fwd_workspace_bytes', B, C, hw), x.device)
+        _lib.call('hk_bilinear_pool_fwd', x, y, None, B, C, hw, ws, ws.numel(), _lib.stream_ptr())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        B, C, H, W = x.shape
+        hw = H * W
+        dy = _f32c(dy)
+        dx = torch.empty_like(x)
+        ws = _ws(_lib.query('hk_bilinear_pool_bwd_workspace_bytes', B, C, hw), x.device)
+        _lib.call('hk_bilinear_pool_bwd', x, dy, dx, B, C, hw, ws, ws.numel(), _lib.stream_ptr())
+        return dx
+
+
+def bilinear_pool(x):
+    return BilinearPoolFn.apply(x)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# nn.Linear as skinny tensor-core GEMMs (BCNN.py:42)
+# ----------------------------------------------------------------------------------------------------------
+class LinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        _check_cuda(x, w, b)
+        x, w = _f32c(x), _f32c(w)
+        B, F = x.shape
+        N = w.shape[0]
+        y = torch.empty(B, N, device=x.device, dtype=torch.float32)
+        ws = _ws(_lib.query('hk_linear_fwd_workspace_bytes', B, F, N), x.device)
+        _lib.call('hk_linear_fwd', x, w, b, y, B, F, N, ws, ws.numel(), _lib.stream_ptr())
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _f32c(dy)
+        B, F = x.shape
+        N = w.shape[0]
+        s = _lib.stream_ptr()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _lib.call('hk_linear_dgrad', dy, w, dx, B, F, N, s)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            db = torch.empty(N, device=x.device, dtype=torch.float32) if ctx.has_bias else None
+            _lib.call('hk_linear_wgrad', dy, x, dw, db, B, F, N, s)
+        return dx, dw, db
+
+
+def linear(x, w, b):
+    return LinearFn.apply(x, w, b)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CrossEntropyLoss(label_smoothing) (train.py:211-212)
+# ----------------------------------------------------------------------------------------------------------
+class CrossEntropyLSFn(Function):
+    @staticmethod
+    def forward(ctx, logits, labels, smoothing):
+        _check_cuda(logits, labels)
+        logits = _f32c(logits)
+        labels = labels.contiguous().to(torch.int64)
+        B, K = logits.shape
+        loss = torch.empty(1, device=logits.device, dtype=torch.float32)
+        dlogits = torch.empty_like(logits)
+        correct = torch.empty(1, device=logits.device, dtype=torch.int32)
+        _lib.call('hk_softmax_ce_ls', logits, labels, loss, dlogits, correct, B, K, float(smoothing), 1.0,
+                  _lib.stream_ptr())
+        ctx.save_for_backward(dlogits)
+        ctx.correct = correct
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g, None, None
+
+
+class CrossEntropyLS(torch.nn.Module):
+    """Drop-in for ``torch.nn.CrossEntropyLoss(label_smoothing=...)`` (mean reduction) on the fused kernel."""
+
+    def __init__(self, label_smoothing=0.1):
+        super().__init__()
+        self.label_smoothing = label_smoothing
+
+    def forward(self, logits, labels):
+        return CrossEntropyLSFn.apply(logits, labels, self.label_smoothing)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# VGG-style backbone (reference model/backbone/vgg.py:56-70), whole feature stack as ONE autograd node
+# ----------------------------------------------------------------------------------------------------------
+def _vgg_plan(cfg):
+    """-> list of ('conv', cout) / ('pool',) entries."""
+    return [('pool',) if v == 'M' else ('conv', int(v)) for v in cfg]
+
+
+class VGGFeaturesFn(Function):
+    """x NCHW image -> NCHW feature map.  Internally NHWC; convs are tcgen05 implicit GEMMs.
+
+    params = (w0, b0, w1, b1, ...) in the reference layout [Cout,Cin,3,3] / [Cout].
+    """
+
+    @staticmethod
+    def forward(ctx, x, cfg, train_backbone, *params):
+        _check_cuda(x, *params)
+        x = _f32c(x)
+        s = _lib.stream_ptr()
+        dev = x.device
+        N, cin0, H, W = x.shape
+        if cin0 != 3:
+            raise _lib.HawkeyeLibError('VGG features expect a 3-channel NCHW image')
+        plan = _vgg_plan(cfg)
+        if plan[-1][0] != 'pool':
+            raise _lib.HawkeyeLibError('VGG cfg must end with a max-pool (reference BCNN keeps the last pool)')
+        save = bool(train_backbone) and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        records = []   # per layer: dict for backward
+        cur, C, li = None, 3, 0
+        for idx, ent in enumerate(plan):
+            if ent[0] == 'conv':
+                cout = ent[1]
+                w, b = _f32c(params[2 * li]), params[2 * li + 1]
+                y = torch.empty(N, H, W, cout, device=dev, dtype=torch.float32)
+                if li == 0:
+                    _lib.call('hk_conv3x3_first_fwd', x, w, b, y, N, H, W, cout, s)
+                    rec = dict(kind='conv0', inp=None, out=y, H=H, W=W, cin=3, cout=cout)
+                else:
+                    wf = torch.empty(9 * cout * C, device=dev, dtype=torch.float32)
+                    wd = torch.empty(9 * cout * C, device=dev, dtype=torch.float32) if save else None
+                    _lib.call('hk_conv3x3_pack_weights', w, wf, wd, cout, C, s)
+                    _lib.call('hk_conv3x3_fwd', cur, wf, b, y, N, H, W, C, cout, 1, s)
+                    rec = dict(kind='conv', inp=cur, out=y, wd=wd, H=H, W=W, cin=C, cout=cout,
+                               inp_is_relu=(records[-1]['kind'] != 'pool'))
+                records.append(rec)
+                cur, C = y, cout
+                li += 1
+            else:
+                last = idx == len(plan) - 1
+                Ho, Wo = H // 2, W // 2
+                out = torch.empty((N, C, Ho, Wo) if last else (N, Ho, Wo, C), device=dev, dtype=torch.float32)
+                _lib.call('hk_maxpool2x2_fwd', cur, out, N, H, W, C, 1 if last else 0, s)
+                records.append(dict(kind='pool', inp=cur, H=H, W=W, C=C, last=last))
+                cur, H, W = out, Ho, Wo
+        if save:
+            ctx.records = records
+            ctx.x = x
+            ctx.N = N
+        else:
+            ctx.records = None
+        ctx.nparams = len(params)
+        return cur
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        if ctx.records is None:
+            return (None, None, None) + (None,) * ctx.nparams
+        s = _lib.stream_ptr()
+        N = ctx.N
+        dev = dfeat.device
+        g = _f32c(dfeat)
+        grads = [None] * ctx.nparams
+        li = ctx.nparams // 2
+        for rec in reversed(ctx.records):
+            if rec['kind'] == 'pool':
+                dx = torch.empty_like(rec['inp'])
+                _lib.call('hk_maxpool2x2_bwd', rec['inp'], g, dx, N, rec['H'], rec['W'], rec['C'],
+                          1 if rec['last'] else 0, s)
+                g = dx
+                continue
+            li -= 1
+            H, W, cin, cout = rec['H'], rec['W'], rec['cin'], rec['cout']
+            dw = torch.empty(cout, cin, 3, 3, device=dev, dtype=torch.float32)
+            db = torch.empty(cout, device=dev, dtype=torch.float32)
+            if rec['kind'] == 'conv0':
+                _lib.call('hk_conv3x3_first_wgrad', ctx.x, g, dw, db, N, H, W, cout, s)
+            else:
+                ws = _ws(_lib.query('hk_conv3x3_wgrad_workspace_bytes', cin, cout), dev)
+                _lib.call('hk_conv3x3_wgrad', rec['inp'], g, dw, db, N, H, W, cin, cout, ws, ws.numel(), s)
+                dx = torch.empty_like(rec['inp'])
+                mask = rec['inp'] if rec['inp_is_relu'] else None
+                _lib.call('hk_conv3x3_dgrad', g, rec['wd'], mask, dx, N, H, W, cin, cout, s)
+                g = dx
+            grads[2 * li], grads[2 * li + 1] = dw, db
+            rec['out'] = None
+        ctx.records = None
+        return (None, None, None) + tuple(grads)
+
+
+def vgg_features(x, cfg, params, train_backbone=True):
+    return VGGFeaturesFn.apply(x, tuple(cfg), bool(train_backbone), *params)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# raw helpers used by tests / other heads
+# ----------------------------------------------------------------------------------------------------------
+def gemm_tf32(A, B, a_mn=False, b_mn=False, M=None, N=None, K=None, alpha=1.0, diag=0.0, D=None, beta=0.0,
+              alpha_vec=None, beta_vec=None, trans_c=False, relu=False, out=None):
+    """Batched C = alpha*A.B + diag*I + beta*D on the tcgen05 GEMM.  A: [b,M,K] (or [b,K,M] if a_mn),
+    B: [b,N,K] (K-major, i.e. C = A.B^T layout) or [b,K,N] if b_mn.  2-D operands are shared across the batch."""
+    _check_cuda(A, B)
+    A, B = _f32c(A), _f32c(B)
+    batch = max(A.shape[0] if A.dim() == 3 else 1, B.shape[0] if B.dim() == 3 else 1)
+    a2, b2 = A.shape[-2:], B.shape[-2:]
+    M_ = a2[1] if a_mn else a2[0]
+    K_ = a2[0] if a_mn else a2[1]
+    N_ = b2[1] if b_mn else b2[0]
+    M, N, K = M or M_, N or N_, K or K_
+    sA = a2[0] * a2[1] if A.dim() == 3 else 0
+    sB = b2[0] * b2[1] if B.dim() == 3 else 0
+    if out is None:
+        out = torch.empty((batch, N, M) if trans_c else (batch, M, N), device=A.device, dtype=torch.float32)
+    ldc = out.shape[-1]
+    sD = ldd = 0
+    if D is not None:
+        D = _f32c(D)
+        ldd = D.shape[-1] if D.shape[-2] != 1 else 0
+        sD = D.shape[-2] * D.shape[-1] if D.dim() == 3 else 0
+    _lib.call('hk_gemm_tf32', A, int(a_mn), a2[1], sA, B, int(b_mn), b2[1], sB, out, ldc, out.shape[-2] * out.shape[-1],
+              int(trans_c), M, N, K, batch, float(alpha), alpha_vec, float(diag), D, ldd, sD, float(beta), beta_vec,
+              int(relu), _lib.stream_ptr())
+    return out

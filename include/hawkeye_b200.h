@@ -1,0 +1,95 @@
+/* hawkeye_b200 — C ABI of the B200-native high-order-pooling hot path.
+ *
+ * One shared library (hawkeye_b200/libhawkeye_b200.so), plain C types, no torch types.
+ * Conventions:
+ *   - return 0 = success; <0 = argument/shape/alignment error, nothing was launched;
+ *     >0 = cudaError_t from a launch.  hk_last_error() gives the text (thread-local).
+ *   - the caller owns every device buffer including workspaces (query *_workspace_bytes);
+ *     the library allocates nothing and never synchronises; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*).
+ *   - tensors are contiguous fp32; pointers 16-byte aligned; no CPU fallback: an unsupported
+ *     shape is an error (-3), never a silent slow path.
+ * Each entry point cites the reference interface it replaces (paths relative to the Hawkeye tree).
+ */
+#ifndef HAWKEYE_B200_H
+#define HAWKEYE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* hk_version(void);
+const char* hk_last_error(void);
+long long hk_launch_count(void);      /* kernels launched by this library on the calling thread */
+void hk_reset_launch_count(void);
+
+/* ---- generic batched TF32 tensor-core GEMM (tcgen05 + TMA) -------------------------------------
+ * C[b] = alpha*alpha_vec[b] * A[b].B[b] + diag*I + beta*beta_vec[b] * D[b]   (ReLU optional; C optionally transposed)
+ * A logical [M,K]: a_mn_major=0 -> A[m*lda+k]; 1 -> A[k*lda+m].   B logical [K,N]: b_mn_major=0 -> B[n*ldb+k]; 1 -> B[k*ldb+n].
+ * Replaces torch.bmm call sites model/methods/MPNCOV.py:117,132,154-160,178-194 and 1x1 convs resnet.py:34-37. */
+int hk_gemm_tf32(const float* A, int a_mn_major, long long lda, long long strideA, const float* B, int b_mn_major,
+                 long long ldb, long long strideB, float* C, long long ldc, long long strideC, int trans_c, int M,
+                 int N, int K, int batch, float alpha, const float* alpha_vec, float diag, const float* D,
+                 long long ldd, long long strideD, float beta, const float* beta_vec, int relu, void* stream);
+
+/* ---- BCNN bilinear pooling: model/methods/BCNN.py:13-27 (BilinearPooling.forward) ----------------
+ * x [B,C,HW] (NCHW feature map viewed as in BCNN.py:17) -> y [B,C*C] = normalize(sqrt(x x^T/HW + 1e-5)).
+ * inv_norm_out (optional, [B]) receives 1/||z||.  Requires C%128==0, HW%4==0. */
+size_t hk_bilinear_pool_fwd_workspace_bytes(int B, int C, int HW);
+int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, int C, int HW, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* backward of the same (what autograd derives for BCNN.py:13-27): dx [B,C,HW] from dy [B,C*C]; z is recomputed. */
+size_t hk_bilinear_pool_bwd_workspace_bytes(int B, int C, int HW);
+int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int C, int HW, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---- VGG-16 backbone: model/backbone/vgg.py:56-70 (Conv2d 3x3 s1 p1 + bias, ReLU, MaxPool2d(2,2)) ----------
+ * Activations are NHWC fp32 inside the backbone.  Weights keep the reference layout [Cout,Cin,3,3] in the
+ * state_dict and are re-packed per step: w_fwd [9][Cout][Cin], w_dgrad [9][Cin][Cout] (taps flipped). */
+int hk_conv3x3_pack_weights(const float* w, float* w_fwd, float* w_dgrad, int Cout, int Cin, void* stream);
+/* y = relu?(conv3x3(x, w) + bias): implicit GEMM on tcgen05, TMA zero-fill = padding.  Cin%32==0, Cout%32==0. */
+int hk_conv3x3_fwd(const float* x_nhwc, const float* w_fwd_packed, const float* bias, float* y_nhwc, int N, int H,
+                   int W, int Cin, int Cout, int relu, void* stream);
+/* dx = conv3x3^T(dy, w) * (relu_mask_act > 0)  (mask optional: the ReLU output that produced x) */
+int hk_conv3x3_dgrad(const float* dy_nhwc, const float* w_dgrad_packed, const float* relu_mask_act, float* dx_nhwc,
+                     int N, int H, int W, int Cin, int Cout, void* stream);
+/* dw [Cout,Cin,3,3] (reference layout), db [Cout] (optional) from x, dy (dy already ReLU-masked).  Cin%64==0. */
+size_t hk_conv3x3_wgrad_workspace_bytes(int Cin, int Cout);
+int hk_conv3x3_wgrad(const float* x_nhwc, const float* dy_nhwc, float* dw, float* db, int N, int H, int W, int Cin,
+                     int Cout, void* workspace, size_t workspace_bytes, void* stream);
+/* first layer (Cin=3): NCHW image in, NHWC out, bias+ReLU fused; and its weight/bias gradient */
+int hk_conv3x3_first_fwd(const float* x_nchw, const float* w, const float* bias, float* y_nhwc, int N, int H, int W,
+                         int Cout, void* stream);
+int hk_conv3x3_first_wgrad(const float* x_nchw, const float* dy_nhwc, float* dw, float* db, int N, int H, int W,
+                           int Cout, void* stream);
+/* MaxPool2d(2,2) on NHWC; out_nchw=1 writes the pooled map as NCHW (input of the pooling heads).
+ * bwd routes dy to the first max (PyTorch semantics) and multiplies by (x>0), i.e. also applies the ReLU backward. */
+int hk_maxpool2x2_fwd(const float* x_nhwc, float* y, int N, int H, int W, int C, int out_nchw, void* stream);
+int hk_maxpool2x2_bwd(const float* x_nhwc, const float* dy, float* dx_nhwc, int N, int H, int W, int C, int dy_nchw,
+                      void* stream);
+int hk_relu_mask_inplace(float* dy, const float* act, size_t n, void* stream);
+
+/* ---- classifier nn.Linear (BCNN.py:42, CBCNN.py:26, MPNCOV.py:31) as skinny tcgen05 GEMMs ------------------- */
+size_t hk_linear_fwd_workspace_bytes(int B, int F, int N);
+int hk_linear_fwd(const float* x, const float* w, const float* bias, float* y, int B, int F, int N, void* workspace,
+                  size_t workspace_bytes, void* stream);
+int hk_linear_dgrad(const float* dy, const float* w, float* dx, int B, int F, int N, void* stream);
+int hk_linear_wgrad(const float* dy, const float* x, float* dw, float* db, int B, int F, int N, void* stream);
+
+/* ---- nn.CrossEntropyLoss(label_smoothing) fwd+bwd (train.py:211-212, :315-319); labels int64 ----------------
+ * loss[0] = mean loss; dlogits (optional) = dloss/dlogits * grad_scale; correct (optional) = #argmax==label. */
+int hk_softmax_ce_ls(const float* logits, const long long* labels, float* loss, float* dlogits, int* correct, int B,
+                     int K, float label_smoothing, float grad_scale, void* stream);
+
+/* ---- optimizers over flat fp32 buffers: torch.optim.SGD (Examples/BCNN.py:40), Adam (Examples/MPN.py:14-18) */
+int hk_sgd_momentum(float* p, const float* g, float* buf, size_t n, float lr, float momentum, float weight_decay,
+                    float grad_scale, int first_step, void* stream);
+int hk_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+            float weight_decay, float grad_scale, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAWKEYE_B200_H */
