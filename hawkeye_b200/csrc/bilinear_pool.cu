@@ -44,7 +44,8 @@ __global__ void colsum_partial_kernel(const float* __restrict__ X, float* __rest
   for (int p = threadIdx.x; p < HW; p += blockDim.x) {
     float s = 0.f;
 #pragma unroll 8
-    for (int c = c0; c < c1; ++c) s += xb[(size_t)c * HW + p];
+    for (int c = c0; c < c1; ++c)  // sum what the tensor core will see: kind::tf32 truncates the low 13 mantissa bits
+      s += __uint_as_float(__float_as_uint(xb[(size_t)c * HW + p]) & 0xffffe000u);
     partial[((size_t)b * CS + cs) * HW + p] = s;
   }
 }

@@ -166,16 +166,23 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 //   K-major operand : rows of 128 B (32 fp32 of K), 8-row groups SBO bytes apart (1024); LBO unused.
 //   MN-major operand: k-rows of 128 B (32 fp32 of M/N), 8 k-rows = one 1024 B atom; the next
 //                     32 M/N elements are LBO bytes away, the next 8 k-rows SBO bytes away.
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//                     For 32-bit (tf32) data the MN-major layout is SWIZZLE_128B_BASE32B (type 1): 32 B chunks
+//                     swizzled over 4 k-rows (512 B atom), so SBO = 512 for contiguous k-rows.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                               uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
 }
 // Instruction descriptor for kind::tf32, fp32 accumulate.
+// MN-major tf32 operand: `mn_block_stride` bytes between consecutive 32-element M/N blocks; k-rows contiguous.
+__device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr, uint32_t mn_block_stride) {
+  return make_sdesc(saddr, mn_block_stride, 512, 1);
+}
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |

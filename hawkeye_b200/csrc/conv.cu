@@ -189,11 +189,12 @@ static void pick_tile(int W, int H, int N, int target, int* TW, int* TH, int* TN
   (void)N;
 }
 
-static int make_act_map(CUtensorMap* tm, const float* X, int N, int H, int W, int C, int TW, int TH, int TN) {
+static int make_act_map(CUtensorMap* tm, const float* X, int N, int H, int W, int C, int TW, int TH, int TN,
+                        bool mn_major = false) {
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
   uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
   uint32_t box[4] = {32, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
-  return make_tmap(tm, X, 4, dims, strides, box);
+  return make_tmap(tm, X, 4, dims, strides, box, mn_major);
 }
 
 template <int BN>
@@ -334,8 +335,8 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
           const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
 #pragma unroll
           for (int ks = 0; ks < Cfg::KP / 8; ++ks)
-            umma_tf32_ss(tmem_base, make_sdesc(a_addr + ks * 1024, Cfg::KP * 128, 1024),
-                         make_sdesc(b_addr + ks * 1024, Cfg::KP * 128, 1024), idesc, (kb | ks) ? 1u : 0u);
+            umma_tf32_ss(tmem_base, make_sdesc_mn(a_addr + ks * 1024, Cfg::KP * 128),
+                         make_sdesc_mn(b_addr + ks * 1024, Cfg::KP * 128), idesc, (kb | ks) ? 1u : 0u);
           umma_commit(&empty[s]);
         }
         umma_commit(accf);
@@ -396,8 +397,8 @@ int conv3x3_wgrad(const float* x, const float* dy, float* dwp, int N, int H, int
   a.ksplit = (int)ks;
   CUtensorMap tmDY, tmX;
   int r;
-  if ((r = make_act_map(&tmDY, dy, N, H, W, Cout, a.TW, a.TH, a.TN))) return r;
-  if ((r = make_act_map(&tmX, x, N, H, W, Cin, a.TW, a.TH, a.TN))) return r;
+  if ((r = make_act_map(&tmDY, dy, N, H, W, Cout, a.TW, a.TH, a.TN, true))) return r;
+  if ((r = make_act_map(&tmX, x, N, H, W, Cin, a.TW, a.TH, a.TN, true))) return r;
   cudaError_t e = cudaMemsetAsync(dwp, 0, (size_t)9 * Cout * Cin * sizeof(float), stream);
   if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(dWp): %s", cudaGetErrorString(e));
   if (BN == 128) return launch_wgrad<128>(tmDY, tmX, a, stream);

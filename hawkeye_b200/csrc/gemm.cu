@@ -8,6 +8,8 @@
 //   * the (S . X) contraction of the bilinear / compact-bilinear backward (BCNN.py:13-27, CBCNN.py:96-135),
 //   * 1x1 convolutions in NHWC (model/backbone/resnet.py:29-37).
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host.h"
 #include "../../include/hawkeye_b200.h"
@@ -38,7 +40,7 @@ struct GemmCfg {
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpi epi, int M,
-                 int N, int K, int a_mn, int b_mn, int shareA, int shareB) {
+                 int N, int K, int a_mn, int b_mn, int shareA, int shareB, int mn_sbo, int mn_type) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -109,8 +111,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int krem = K - kb * 32;
         const int ksteps = krem >= 32 ? 4 : (krem + 7) / 8;
         for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t ad = a_mn ? make_sdesc(a_addr + ks * 1024, 4096, 1024) : make_sdesc(a_addr + ks * 32, 16, 1024);
-          const uint64_t bd = b_mn ? make_sdesc(b_addr + ks * 1024, 4096, 1024) : make_sdesc(b_addr + ks * 32, 16, 1024);
+          const uint64_t ad = a_mn ? make_sdesc(a_addr + ks * 1024, 4096, mn_sbo, mn_type) : make_sdesc(a_addr + ks * 32, 16, 1024);
+          const uint64_t bd = b_mn ? make_sdesc(b_addr + ks * 1024, 4096, mn_sbo, mn_type) : make_sdesc(b_addr + ks * 32, 16, 1024);
           umma_tf32_ss(tmem_base, ad, bd, idesc, (kb | ks) ? 1u : 0u);
         }
         umma_commit(&empty[s]);
@@ -182,7 +184,12 @@ static int make_operand_map(CUtensorMap* tm, const float* P, int mn_major, long 
   }
   strides[0] = (uint64_t)ld * 4;
   strides[1] = bs;
-  return make_tmap(tm, P, 3, dims, strides, box);
+  return make_tmap(tm, P, 3, dims, strides, box, mn_major != 0);
+}
+
+static int dbg_env(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
 }
 
 template <int BN>
@@ -196,7 +203,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     attr_set = true;
   }
   dim3 grid((M + 127) / 128, (N + BN - 1) / BN, batch);
-  umma_gemm_kernel<BN><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, epi, M, N, K, a_mn, b_mn, shareA, shareB);
+  umma_gemm_kernel<BN><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, epi, M, N, K, a_mn, b_mn, shareA, shareB, dbg_env("HK_DBG_MN_SBO", 512), dbg_env("HK_DBG_MN_TYPE", 1));
   HK_LAUNCH_CHECK("umma_gemm_kernel");
   return 0;
 }

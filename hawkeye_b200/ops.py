@@ -160,7 +160,7 @@ class VGGFeaturesFn(Function):
         plan = _vgg_plan(cfg)
         if plan[-1][0] != 'pool':
             raise _lib.HawkeyeLibError('VGG cfg must end with a max-pool (reference BCNN keeps the last pool)')
-        save = bool(train_backbone) and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        save = bool(train_backbone)   # decided by the caller: grad mode is always off inside Function.forward
         records = []   # per layer: dict for backward
         cur, C, li = None, 3, 0
         for idx, ent in enumerate(plan):
@@ -234,7 +234,8 @@ class VGGFeaturesFn(Function):
 
 
 def vgg_features(x, cfg, params, train_backbone=True):
-    return VGGFeaturesFn.apply(x, tuple(cfg), bool(train_backbone), *params)
+    save = bool(train_backbone) and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return VGGFeaturesFn.apply(x, tuple(cfg), save, *params)
 
 
 # ----------------------------------------------------------------------------------------------------------
