@@ -8,7 +8,7 @@
 
 namespace hk {
 
-thread_local long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 char* last_error_buf() {
   static thread_local char buf[512] = {0};
@@ -95,7 +95,7 @@ extern "C" {
 
 const char* hk_version(void) { return "hawkeye_b200 0.1 (sm_100a; tcgen05/TMA)"; }
 const char* hk_last_error(void) { return hk::last_error_buf(); }
-long long hk_launch_count(void) { return hk::g_launches; }
-void hk_reset_launch_count(void) { hk::g_launches = 0; }
+long long hk_launch_count(void) { return hk::g_launches.load(); }
+void hk_reset_launch_count(void) { hk::g_launches.store(0); }
 
 }  // extern "C"

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -20,7 +21,7 @@ namespace hk {
 char* last_error_buf();
 int set_error(int code, const char* fmt, ...);
 int check_launch(const char* what);
-extern thread_local long long g_launches;  // kernels launched by this library on this thread
+extern std::atomic<long long> g_launches;  // kernels launched by this library (all host threads)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

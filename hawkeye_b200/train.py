@@ -1,0 +1,288 @@
+"""``Trainer`` with the reference's template-method surface (train.py:37-435) for the hot-path methods.
+
+Same hooks (``get_model / get_criterion / get_optimizer / get_scheduler / to_device / batch_training /
+batch_validate / save_model / save_checkpoint / load_checkpoint / on_*``) and the same yaml schema, so the
+reference's ``Examples/{BCNN,CBCNN,MPN}.py`` subclasses port by changing one import.  Differences, all at the
+edges: data-parallelism is one process per GPU + NCCL gradient all-reduce instead of
+``nn.DataParallel`` (train.py:220-228); the criterion / optimizer are the fused CUDA kernels; ``verbose=`` is not
+passed to ReduceLROnPlateau; a missing ``resize_size`` defaults to image_size/0.875; ``train()`` re-raises.
+The JPEG input pipeline (dataset/*) is out of scope: pass ``dataloaders=`` or run inside a Hawkeye checkout
+whose ``dataset`` package is importable.
+"""
+import logging
+import os
+
+import torch
+
+from . import engine, ops
+from .config import setup_config
+from .registry import MODEL
+from .utils import load_state_dict
+
+
+class AverageMeter:
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.sum, self.count, self.avg = 0.0, 0, 0.0
+
+    def update(self, val, n=1):
+        self.sum += val * n
+        self.count += n
+        self.avg = self.sum / self.count
+
+
+def accuracy(output, target, topk=1):
+    """top-k accuracy in percent (utils/utils.py:52-66)."""
+    with torch.no_grad():
+        _, pred = output.topk(topk, 1, True, True)
+        correct = pred.eq(target.view(-1, 1)).any(dim=1).float().sum()
+        return (correct * (100.0 / target.size(0))).item()
+
+
+class Trainer:
+    def __init__(self, config=None, dataloaders=None):
+        self.config = config if config is not None else setup_config()
+        self.epoch = 0
+        self.start_epoch = 0
+        self.total_epoch = self.config.train.epoch
+        self.log_root = os.path.join(self.config.experiment.log_dir, self.config.experiment.name)
+        self.logger = logging.getLogger('hawkeye_b200')
+        self.rank, self.local_rank, self.world = engine.init_distributed()
+        cuda = self.config.experiment.cuda if isinstance(self.config.experiment.cuda, list) else []
+        if not torch.cuda.is_available():
+            raise RuntimeError('hawkeye_b200 needs a CUDA device (no CPU fallback)')
+        self.device = torch.device('cuda', self.local_rank if self.world > 1 else (cuda[0] if cuda else 0))
+        torch.cuda.set_device(self.device)
+        if 'seed' in self.config.experiment and self.config.experiment.seed is not None:
+            torch.manual_seed(self.config.experiment.seed)
+        self.dataloaders = dataloaders if dataloaders is not None else self.get_dataloader(self.config.dataset)
+        self.model = self.get_model(self.config.model)
+        self.model = self.to_device(self.model, parallel=True)
+        self.criterion = self.get_criterion(self.config.train.criterion)
+        self.flat = self.flatten_parameters()
+        self.allreduce = engine.GradAllReduce(self.flat, early_group=self.early_group(), world=self.world)
+        self.optimizer = self.get_optimizer(self.config.train.optimizer)
+        self.optimizer.grad_scale = 1.0 / self.world
+        self.scheduler = self.get_scheduler(self.config.train.scheduler)
+        self.average_meters = {'acc': AverageMeter(), 'loss': AverageMeter()}
+        if 'resume' in self.config.experiment and self.config.experiment.resume:
+            self.load_checkpoint(self.config.experiment.resume)
+
+    # ---- builders (override like the reference's Examples do) -------------------------------------------
+    def get_model(self, config):
+        model = MODEL.get(config.name)(config)                      # train.py:161-162
+        if 'load' in config and config.load != '':
+            load_state_dict(model, torch.load(config.load, map_location='cpu'))
+        return model
+
+    def get_dataloader(self, config):
+        try:
+            from dataset.dataset import FGDataset  # noqa: F401  (reference package, when run inside Hawkeye)
+        except Exception as e:
+            raise RuntimeError('the image input pipeline is outside this package: pass dataloaders= or run inside a '
+                               'Hawkeye checkout') from e
+        from torch.utils.data import DataLoader
+        from dataset.transforms import ClassificationPresetTrain, ClassificationPresetEval
+        t = config.transformer
+        resize = t['resize_size'] if 'resize_size' in t else int(t['image_size'] / 0.875)
+        tf = {'train': ClassificationPresetTrain(crop_size=t['image_size'], auto_augment_policy='ta_wide',
+                                                 random_erase_prob=0.1),
+              'val': ClassificationPresetEval(crop_size=t['image_size'], resize_size=resize)}
+        ds = {s: FGDataset(config.root_dir, os.path.join(config.meta_dir, s + '.txt'), transform=tf[s])
+              for s in ('train', 'val')}
+        return {s: DataLoader(ds[s], config.batch_size, num_workers=config.num_workers, pin_memory=True,
+                              shuffle=s == 'train') for s in ('train', 'val')}
+
+    def get_criterion(self, config):
+        return ops.CrossEntropyLS(label_smoothing=0.1)              # train.py:211-212
+
+    def param_groups(self):
+        """[(params, lr_multiplier)] — contiguous slices of the flat buffer; the first group listed as ``early`` by
+        ``early_group`` is all-reduced while the rest of backward still runs."""
+        m = self.get_model_module()
+        head = list(m.classifier.parameters()) if hasattr(m, 'classifier') else []
+        ids = {id(p) for p in head}
+        rest = [p for p in m.parameters() if id(p) not in ids]
+        return [(rest, 1.0), (head, 1.0)]
+
+    def early_group(self):
+        gs = [g for g, _ in self.param_groups() if any(p.requires_grad for p in g)]
+        return len(gs) - 1 if len(gs) > 1 else None
+
+    def flatten_parameters(self):
+        groups = [g for g, _ in self.param_groups() if any(p.requires_grad for p in g)]
+        return engine.FlatParams(None, groups=groups)
+
+    def get_optimizer(self, config):
+        name = config.name if 'name' in config else 'Adam'
+        mult = [m for g, m in self.param_groups() if any(p.requires_grad for p in g)]
+        lrs = [config.lr * m for m in mult]
+        wd = config.weight_decay if 'weight_decay' in config else 0.0
+        if name == 'SGD':
+            return engine.FusedSGD(self.flat, lr=config.lr, momentum=config.momentum if 'momentum' in config else 0.0,
+                                   weight_decay=wd, group_lrs=lrs)
+        return engine.FusedAdam(self.flat, lr=config.lr, weight_decay=wd, group_lrs=lrs)   # train.py:214-215
+
+    def get_scheduler(self, config):
+        name = config.name if 'name' in config else ''
+        if name == 'ReduceLROnPlateau':                              # Examples/BCNN.py:42-44 (without verbose=)
+            return _Plateau(self.optimizer, mode='max', factor=0.1, patience=3, threshold=1e-4)
+        return _Cosine(self.optimizer, config.T_max if 'T_max' in config else self.total_epoch,
+                       config.eta_min if 'eta_min' in config else 0.0,
+                       config.warmup_epochs if 'warmup_epochs' in config else 0,
+                       config.lr_warmup_decay if 'lr_warmup_decay' in config else 0.01)
+
+    def to_device(self, m, parallel=False):
+        return m.to(self.device, non_blocking=True) if isinstance(m, torch.Tensor) else m.to(self.device)
+
+    def get_model_module(self, model=None):
+        return self.model if model is None else model
+
+    # ---- the hot step (train.py:310-325) ------------------------------------------------------------------------
+    def batch_training(self, data):
+        images, labels = self.to_device(data['img']), self.to_device(data['label'])
+        outputs = self.model(images)
+        loss = self.criterion(outputs, labels)
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.allreduce.finish()
+        self.optimizer.step()
+        acc = accuracy(outputs, labels, 1)
+        self.average_meters['acc'].update(acc, images.size(0))
+        self.average_meters['loss'].update(loss.item(), images.size(0))
+        return loss
+
+    def batch_validate(self, data):
+        images, labels = self.to_device(data['img']), self.to_device(data['label'])
+        with torch.no_grad():
+            logits = self.model(images)
+        self.average_meters['acc'].update(accuracy(logits, labels, 1), images.size(0))
+
+    def validate(self):
+        self.model.train(False)
+        for m in self.average_meters.values():
+            m.reset()
+        for data in self.dataloaders['val']:
+            self.batch_validate(data)
+        self.model.train(True)
+
+    def train(self):
+        cfg = self.config.train
+        self.model.train()
+        best = None
+        for epoch in range(self.start_epoch, self.total_epoch):
+            self.epoch = epoch
+            for m in self.average_meters.values():
+                m.reset()
+            self.on_start_epoch(None)
+            for data in self.dataloaders['train']:
+                self.on_start_forward(None)
+                self.batch_training(data)
+                self.on_end_forward(None)
+            self.validate()
+            val_acc = self.average_meters['acc'].avg
+            is_best = epoch >= 5 and (best is None or val_acc > best)      # train.py:284-288
+            best = val_acc if best is None else max(best, val_acc)
+            self.do_scheduler_step()
+            if self.rank == 0:
+                if epoch != 0 and (epoch + 1) % cfg.save_frequence == 0:
+                    self.save_model()
+                if is_best:
+                    self.save_model('best_model.pth')
+            self.on_end_epoch(None)
+
+    def do_scheduler_step(self):
+        if isinstance(self.scheduler, _Plateau):
+            self.scheduler.step(self.average_meters['acc'].avg)
+        else:
+            self.scheduler.step()
+
+    # ---- checkpoint formats identical to the reference (train.py:369-395): plain state_dict .pth ---------------------
+    def save_model(self, name=None):
+        os.makedirs(self.log_root, exist_ok=True)
+        path = os.path.join(self.log_root, name or f'{self.config.model.name}_epoch_{self.epoch + 1}.pth')
+        torch.save({k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()}, path)
+        return path
+
+    def save_checkpoint(self):
+        os.makedirs(self.log_root, exist_ok=True)
+        path = os.path.join(self.log_root, f'checkpoint_epoch_{self.epoch}.pth')
+        torch.save({'epoch': self.epoch,
+                    'model': {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()},
+                    'optimizer': self.optimizer.state_dict(), 'scheduler': self.scheduler.state_dict()}, path)
+        return path
+
+    def load_checkpoint(self, path):
+        ck = torch.load(path, map_location='cpu')
+        self.start_epoch = ck['epoch']
+        load_state_dict(self.model, ck['model'])
+        self.optimizer.load_state_dict(ck['optimizer'])
+        self.scheduler.load_state_dict(ck['scheduler'])
+
+    def on_start_epoch(self, config):
+        pass
+
+    def on_end_epoch(self, config):
+        pass
+
+    def on_start_forward(self, config):
+        pass
+
+    def on_end_forward(self, config):
+        pass
+
+
+class _Plateau:
+    """ReduceLROnPlateau(mode='max') over FusedSGD/FusedAdam param_groups (Examples/BCNN.py:42-48)."""
+
+    def __init__(self, opt, mode='max', factor=0.1, patience=3, threshold=1e-4):
+        self.opt, self.factor, self.patience, self.threshold = opt, factor, patience, threshold
+        self.best, self.bad = None, 0
+
+    def step(self, metric):
+        if self.best is None or metric > self.best * (1 + self.threshold):
+            self.best, self.bad = metric, 0
+        else:
+            self.bad += 1
+            if self.bad > self.patience:
+                for g in self.opt.param_groups:
+                    g['lr'] *= self.factor
+                self.bad = 0
+
+    def state_dict(self):
+        return dict(best=self.best, bad=self.bad)
+
+    def load_state_dict(self, sd):
+        self.best, self.bad = sd['best'], sd['bad']
+
+
+class _Cosine:
+    """LinearLR warm-up -> CosineAnnealingLR (Examples/CBCNN.py:35-45, Examples/MPN.py:20-30; train.py:217-218)."""
+
+    def __init__(self, opt, T_max, eta_min=0.0, warmup_epochs=0, warmup_decay=0.01):
+        import math
+        self.opt, self.T, self.eta, self.w, self.d, self.e, self.math = opt, T_max, eta_min, warmup_epochs, warmup_decay, 0, math
+        self._apply()
+
+    def _apply(self):
+        for g in self.opt.param_groups:
+            base = g['initial_lr']
+            if self.e < self.w:
+                f = self.d + (1 - self.d) * self.e / max(self.w, 1)
+                g['lr'] = base * f
+            else:
+                t = self.e - self.w
+                g['lr'] = self.eta + (base - self.eta) * (1 + self.math.cos(self.math.pi * t / max(self.T - self.w, 1))) / 2
+
+    def step(self):
+        self.e += 1
+        self._apply()
+
+    def state_dict(self):
+        return dict(e=self.e)
+
+    def load_state_dict(self, sd):
+        self.e = sd['e']
+        self._apply()
