@@ -82,6 +82,11 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def host_threads():
+    """Threads for the CPU arm: all cores up to 32 (a batch-2 step stops scaling, and oversubscribes, beyond that)."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def cpu_step_port(stage, B, threads, steps):
     """The oracle port of the reference step on the host cores (test/bench infrastructure, never the product)."""
     import detgen
@@ -111,7 +116,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     B = 2
     ips, dt = cpu_step_port(args.stage, B, threads, max(1, min(args.steps, 3)))
     line = {
@@ -161,6 +166,7 @@ def main():
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--impl', default='native')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='profiling runs only')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
@@ -224,9 +230,12 @@ def main():
 
     # end to end through the public Trainer API with host inputs
     data = {'img': x_host, 'label': y_host}
-    for _ in range(2):
-        tr.batch_training(data)
-    ms_e2e = timed(lambda: tr.batch_training(data), args.steps)
+    if args.no_e2e:
+        ms_e2e = float('nan')
+    else:
+        for _ in range(2):
+            tr.batch_training(data)
+        ms_e2e = timed(lambda: tr.batch_training(data), args.steps)
     e2e = B * world * args.steps / (ms_e2e * 1e-3)
     final_loss = float(loss.item())
 
@@ -235,8 +244,11 @@ def main():
             dist.destroy_process_group()
         return
     hbm_peak, tf_peak, which = measured_peaks()
-    t_avg, t_med = time_bilinear_kernel(32)
-    t256, _ = time_bilinear_kernel(256, iters=8)
+    if args.no_e2e:
+        t_avg, t256 = float('nan'), float('nan')
+    else:
+        t_avg, t_med = time_bilinear_kernel(32)
+        t256, _ = time_bilinear_kernel(256, iters=8)
     ach = 32 * K1_FWD_BYTES_PER_IMG / t_avg / 1e9
     ach256 = 256 * K1_FWD_BYTES_PER_IMG / t256 / 1e9
     flops_img = VGG16_FWD_GFLOP_PER_IMG * (3.0 if args.stage == 2 else 1.0) * 1e9
@@ -263,7 +275,7 @@ def main():
                           'note': 'peak = measured bf16 sustained / 2 (tf32 runs at half the bf16 rate)'},
     }
     if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         ips, dt = cpu_step_port(args.stage, 2, threads, 2)
         line['cpu_baseline'] = {'value': ips, 'unit': 'img/s', 'cores': threads, 'kind': 'port',
                                 'sample': f'2 timed steps of batch 2 ({dt:.2f} s/step), torch-CPU oracle port of the '

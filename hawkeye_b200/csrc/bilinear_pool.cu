@@ -33,6 +33,10 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 // partial[b][cs][p] = sum_{c in split cs} x[b][c][p];  also zeroes the per-image scalars used by the backward.
 __global__ void colsum_partial_kernel(const float* __restrict__ X, float* __restrict__ partial, int C, int HW, int CS,
                                       float* zero_a, float* zero_b, int zero_n) {
+  // let the dependent Gram kernel (launched with programmatic stream serialization) start its TMA/MMA pipeline now;
+  // it only needs our result in its epilogue (griddepcontrol.wait there).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  extern __shared__ float red[];  // [nrl][HW]
   const int b = blockIdx.x, cs = blockIdx.y;
   if (cs == 0 && threadIdx.x < zero_n) {
     if (zero_a) zero_a[b * zero_n + threadIdx.x] = 0.f;
@@ -40,12 +44,29 @@ __global__ void colsum_partial_kernel(const float* __restrict__ X, float* __rest
   }
   const int cper = (C + CS - 1) / CS;
   const int c0 = cs * cper, c1 = min(C, c0 + cper);
-  const float* xb = X + (size_t)b * C * HW;
+  const int Q = HW / 4;                                   // float4 columns per row (HW % 4 == 0)
+  const int nrl = (int)blockDim.x / Q > 0 ? (int)blockDim.x / Q : 1;  // row lanes
+  const int rl = nrl > 1 ? (int)threadIdx.x / Q : 0;
+  const float4* xb = reinterpret_cast<const float4*>(X + (size_t)b * C * HW);
+  if (rl < nrl) {
+    for (int q = nrl > 1 ? (int)threadIdx.x % Q : (int)threadIdx.x; q < Q; q += (nrl > 1 ? Q : (int)blockDim.x)) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int c = c0 + rl; c < c1; c += nrl) {
+        // sum what the tensor core will see: kind::tf32 truncates the low 13 mantissa bits
+        const float4 v = __ldg(xb + (size_t)c * Q + q);
+        s.x += __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        s.y += __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        s.z += __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        s.w += __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+      }
+      reinterpret_cast<float4*>(red + (size_t)rl * HW)[q] = s;
+    }
+  }
+  __syncthreads();
   for (int p = threadIdx.x; p < HW; p += blockDim.x) {
     float s = 0.f;
-#pragma unroll 8
-    for (int c = c0; c < c1; ++c)  // sum what the tensor core will see: kind::tf32 truncates the low 13 mantissa bits
-      s += __uint_as_float(__float_as_uint(xb[(size_t)c * HW + p]) & 0xffffe000u);
+    for (int r = 0; r < nrl; ++r) s += red[(size_t)r * HW + p];
     partial[((size_t)b * CS + cs) * HW + p] = s;
   }
 }
@@ -164,7 +185,8 @@ __global__ void __launch_bounds__(192, 2) gram_pair_kernel(const __grid_constant
     const int et = threadIdx.x - 64;  // 0..127
     float inv_norm = 1.f;
     if (MODE == MODE_BCNN_FWD) {
-      // closed-form norm from the channel-sum partials, overlapped with the TMA/MMA pipeline
+      // closed-form norm from the channel-sum partials (K0 may still be running: wait for it here, not at launch)
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       float acc = 0.f;
       const float* pb = a.partial + (size_t)b * a.CS * a.HW;
       for (int p = et; p < a.HW; p += 128) {
@@ -203,18 +225,19 @@ __global__ void __launch_bounds__(192, 2) gram_pair_kernel(const __grid_constant
           const float* dyt = a.dY + (size_t)b * CC + (size_t)jb0 * a.C + ia;   // dY[jb][ia]: coalesced over lanes
           const float4* dyd = reinterpret_cast<const float4*>(a.dY + (size_t)b * CC + (size_t)ia * a.C + jb0);
           float* s = a.S + (size_t)b * CC + (size_t)jb0 * a.C + ia;
-          float dd[32];
+          float dd[32], dtv[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 t = dyd[j];
+            const float4 t = __ldg(dyd + j);
             dd[4 * j] = t.x; dd[4 * j + 1] = t.y; dd[4 * j + 2] = t.z; dd[4 * j + 3] = t.w;
           }
 #pragma unroll
+          for (int j = 0; j < 32; ++j) dtv[j] = __ldg(dyt + (size_t)j * a.C);   // all loads in flight before any store
+#pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float z = fast_sqrt(fmaf(v[j], a.inv_hw, a.eps));
-            const float dt = dyt[(size_t)j * a.C];
-            craw = fmaf(dt, z, craw);
-            s[(size_t)j * a.C] = tf32_round(__fdividef(dt + dd[j], 2.f * z));
+            craw = fmaf(dtv[j], z, craw);
+            s[(size_t)j * a.C] = tf32_round(__fdividef(dtv[j] + dd[j], 2.f * z));
           }
         } else {  // MODE_CBP_FWD: signed scatter of the raw Gram into the d sketch bins
           const int hi = a.h1[ia];
@@ -255,7 +278,23 @@ static int launch_gram(const CUtensorMap& tm, const GramArgs& a, cudaStream_t st
     attr_set = true;
   }
   const int items = a.nblk * (a.nblk - 1) / 2 + (a.nblk + 1) / 2;
-  gram_pair_kernel<MODE><<<dim3(items, a.B), 192, GRAM_SMEM, stream>>>(tm, a);
+  if (MODE == MODE_BCNN_FWD) {
+    // programmatic dependent launch: overlap this kernel's prologue + TMA/MMA pipeline with the channel-sum kernel
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(items, a.B);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = GRAM_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gram_pair_kernel<MODE>, tm, a);
+    if (e != cudaSuccess) return set_error((int)e, "cudaLaunchKernelEx(gram): %s", cudaGetErrorString(e));
+  } else {
+    gram_pair_kernel<MODE><<<dim3(items, a.B), 192, GRAM_SMEM, stream>>>(tm, a);
+  }
   HK_LAUNCH_CHECK("gram_pair_kernel");
   return 0;
 }
@@ -269,7 +308,12 @@ static int check_gram_shape(const char* op, const float* X, int B, int C, int HW
   return 0;
 }
 
-constexpr int COLSUM_SPLITS = 8;
+constexpr int COLSUM_SPLITS = 16;
+static inline size_t colsum_smem(int HW) {
+  const int Q = HW / 4;
+  const int nrl = 256 / Q > 0 ? 256 / Q : 1;
+  return (size_t)nrl * HW * sizeof(float);
+}
 
 // per-batch scalars for the bilinear backward epilogue:  alpha = 1/(n HW),  beta = -(c_raw/n^2) / (n HW)
 __global__ void bilinear_bwd_scalars_kernel(const float* inv_norm, const float* c_raw, float inv_hw, float* alpha,
@@ -337,7 +381,7 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
   float* invn = inv_norm_out ? inv_norm_out : partial + (size_t)B * COLSUM_SPLITS * HW;
   CUtensorMap tm;
   if ((r = make_x_map(&tm, x, B, C, HW))) return r;
-  colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, 0, stream>>>(x, partial, C, HW, COLSUM_SPLITS, nullptr, nullptr, 0);
+  colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, colsum_smem(HW), stream>>>(x, partial, C, HW, COLSUM_SPLITS, nullptr, nullptr, 0);
   HK_LAUNCH_CHECK("colsum_partial_kernel");
   GramArgs a = {};
   a.B = B; a.C = C; a.HW = HW; a.nblk = C / 128;
@@ -369,7 +413,7 @@ int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int 
   float* beta = alpha + B;
   CUtensorMap tm;
   if ((r = make_x_map(&tm, x, B, C, HW))) return r;
-  colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, 0, stream>>>(x, partial, C, HW, COLSUM_SPLITS, craw, nullptr, 1);
+  colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, colsum_smem(HW), stream>>>(x, partial, C, HW, COLSUM_SPLITS, craw, nullptr, 1);
   HK_LAUNCH_CHECK("colsum_partial_kernel");
   // s_p = sum_c x_cp (also the rank-1 correction vector of the backward); the norm follows in closed form
   colsum_finish_kernel<<<B, 256, 0, stream>>>(partial, svec, COLSUM_SPLITS, HW);
@@ -390,3 +434,137 @@ int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int 
 
 }  // extern "C"
 
+
+// =====================================================================================================
+// Compact bilinear pooling (reference model/methods/CBCNN.py:96-135) via the Gram-scatter identity:
+//   sum_p ifft(fft(x_p S1) * fft(x_p S2)).real [k]  ==  sum_{i,j : (h1[i]+h2[j]) mod d = k} s1[i] s2[j] (X X^T)[i][j]
+// so the forward is the same tcgen05 Gram (MODE_CBP_FWD epilogue scatters into the d bins), followed by
+// signed-sqrt (eps 1e-10, CBCNN.py:132) + L2 normalise (:133); no [B*HW, d] sketch or FFT intermediates ever
+// touch HBM (algorithmic traffic: read X, write d floats per image).
+// =====================================================================================================
+namespace hk {
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+  __syncthreads();
+  return t;
+}
+
+// y = normalize(sign(pre) * sqrt(|pre| + 1e-10)); one block per image
+__global__ void cbp_finalize_fwd_kernel(const float* __restrict__ pre, float* __restrict__ y, int d) {
+  __shared__ float red[32];
+  const float* p = pre + (size_t)blockIdx.x * d;
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) acc += fabsf(p[k]) + 1e-10f;   // s_k^2 = |pre_k| + eps (0 if pre==0)
+  // sign(0) = 0 in torch: those bins contribute 0, not eps
+  float corr = 0.f;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) corr += (p[k] == 0.f) ? 1e-10f : 0.f;
+  const float n2 = block_sum_256(acc - corr, red);
+  const float inv = 1.f / fmaxf(sqrtf(n2), 1e-12f);
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    const float v = p[k];
+    const float s = (v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f)) * sqrtf(fabsf(v) + 1e-10f);
+    y[(size_t)blockIdx.x * d + k] = tf32_round(s * inv);
+  }
+}
+
+// dpre = d/dpre [ normalize(sign(p) sqrt(|p|+eps)) ]^T dy
+__global__ void cbp_finalize_bwd_kernel(const float* __restrict__ pre, const float* __restrict__ dy,
+                                        float* __restrict__ dpre, int d) {
+  __shared__ float red[32];
+  const float* p = pre + (size_t)blockIdx.x * d;
+  const float* g = dy + (size_t)blockIdx.x * d;
+  float n2 = 0.f, dot = 0.f;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    const float v = p[k];
+    if (v != 0.f) {
+      const float r = sqrtf(fabsf(v) + 1e-10f);
+      n2 += r * r;
+      dot += (v > 0.f ? r : -r) * g[k];
+    }
+  }
+  n2 = block_sum_256(n2, red);
+  dot = block_sum_256(dot, red);
+  const float n = fmaxf(sqrtf(n2), 1e-12f);
+  const float c = dot / n;                     // <y, dy>
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    const float v = p[k];
+    float o = 0.f;
+    if (v != 0.f) {
+      const float r = sqrtf(fabsf(v) + 1e-10f);
+      const float s = v > 0.f ? r : -r;
+      const float ds = (g[k] - (s / n) * c) / n;
+      o = ds / (2.f * r);
+    }
+    dpre[(size_t)blockIdx.x * d + k] = o;
+  }
+}
+
+// S[b][i][j] = dG[i][j] + dG[j][i],  dG[i][j] = s1[i] s2[j] dpre[b][(h1[i]+h2[j]) mod d]
+__global__ void cbp_build_s_kernel(const float* __restrict__ dpre, const int* __restrict__ h1,
+                                   const int* __restrict__ h2, const float* __restrict__ s1,
+                                   const float* __restrict__ s2, float* __restrict__ S, int C, int d) {
+  const int b = blockIdx.y;
+  const float* dp = dpre + (size_t)b * d;
+  const size_t n = (size_t)C * C;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / C), j = (int)(e % C);
+    int k1 = h1[i] + h2[j];
+    if (k1 >= d) k1 -= d;
+    int k2 = h1[j] + h2[i];
+    if (k2 >= d) k2 -= d;
+    S[(size_t)b * n + e] = tf32_round(s1[i] * s2[j] * dp[k1] + s1[j] * s2[i] * dp[k2]);
+  }
+}
+
+}  // namespace hk
+
+extern "C" {
+
+int hk_cbp_fwd(const float* x, const int* h1, const int* h2, const float* s1, const float* s2, float* y, float* pre,
+               int B, int C, int HW, int d, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int r = check_gram_shape("hk_cbp_fwd", x, B, C, HW);
+  if (r) return r;
+  HK_REQUIRE(h1 && h2 && s1 && s2 && y && pre && d > 0, HK_ERR_ARG, "hk_cbp_fwd: null pointer / bad d");
+  cudaError_t e = cudaMemsetAsync(pre, 0, (size_t)B * d * sizeof(float), stream);
+  if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(pre): %s", cudaGetErrorString(e));
+  CUtensorMap tm;
+  if ((r = make_x_map(&tm, x, B, C, HW))) return r;
+  GramArgs a = {};
+  a.B = B; a.C = C; a.HW = HW; a.nblk = C / 128;
+  a.inv_hw = 1.f; a.eps = 0.f;
+  a.h1 = h1; a.h2 = h2; a.s1 = s1; a.s2 = s2; a.bins = pre; a.d = d;
+  if ((r = launch_gram<MODE_CBP_FWD>(tm, a, stream))) return r;
+  cbp_finalize_fwd_kernel<<<B, 256, 0, stream>>>(pre, y, d);
+  HK_LAUNCH_CHECK("cbp_finalize_fwd_kernel");
+  return 0;
+}
+
+size_t hk_cbp_bwd_workspace_bytes(int B, int C, int d) { return ((size_t)B * C * C + (size_t)B * d) * sizeof(float); }
+
+int hk_cbp_bwd(const float* x, const float* pre, const float* dy, const int* h1, const int* h2, const float* s1,
+               const float* s2, float* dx, int B, int C, int HW, int d, void* workspace, size_t workspace_bytes,
+               void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int r = check_gram_shape("hk_cbp_bwd", x, B, C, HW);
+  if (r) return r;
+  HK_REQUIRE(pre && dy && dx && h1 && h2 && s1 && s2, HK_ERR_ARG, "hk_cbp_bwd: null pointer");
+  HK_REQUIRE(workspace && workspace_bytes >= hk_cbp_bwd_workspace_bytes(B, C, d), HK_ERR_WORKSPACE,
+             "hk_cbp_bwd: workspace too small");
+  float* S = static_cast<float*>(workspace);
+  float* dpre = S + (size_t)B * C * C;
+  cbp_finalize_bwd_kernel<<<B, 256, 0, stream>>>(pre, dy, dpre, d);
+  HK_LAUNCH_CHECK("cbp_finalize_bwd_kernel");
+  cbp_build_s_kernel<<<dim3(148, B), 256, 0, stream>>>(dpre, h1, h2, s1, s2, S, C, d);
+  HK_LAUNCH_CHECK("cbp_build_s_kernel");
+  // dX = (dG + dG^T) . X      (M = C, K = C, N = HW; X is the MN-major B operand)
+  return hk_gemm_tf32(S, 0, C, (long long)C * C, x, 1, HW, (long long)C * HW, dx, HW, (long long)C * HW, 0, C, HW, C, B,
+                      1.f, nullptr, 0.f, nullptr, 0, 0, 0.f, nullptr, 0, stream_);
+}
+
+}  // extern "C"

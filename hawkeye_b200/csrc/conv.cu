@@ -241,62 +241,70 @@ int conv3x3_igemm(const float* x, const float* wp, const float* bias, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight gradient: dWp[tap][co][ci] += sum over this CTA's pixel tiles of dY[pix,co] * X[pix+tap,ci]
-// A = dY (M = co, MN-major), B = X shifted (N = ci, MN-major); 64 pixels (k) per pipeline stage.
+// weight gradient: one CTA accumulates dWp[tap][co0:co0+128][ci0:ci0+32] for ALL 9 taps over its share of the
+// pixels (split-K across CTAs, fp32 atomics at the end).
+//   A = dY tile (M = 128 co, MN-major, k = 64 pixels)  — loaded once per pixel tile and reused by the 9 taps;
+//   B = X halo patch, one TMA load per kw shift: (TH+2) x TW pixels x 32 ci; the three kh taps are the SAME
+//       shared-memory patch addressed kh*TW rows further down (a whole number of 512 B swizzle atoms), so the
+//       input is fetched 3x (+halo) instead of 9x;
+//   D = 9 accumulators of 128 x 32 fp32 in TMEM (288 columns) + one 128 x 16 accumulator against an all-ones
+//       B tile, whose every column is sum_pix dY[pix,co] = the bias gradient (no separate pass over dY).
 // ------------------------------------------------------------------------------------------------
 struct WgradArgs {
-  float* dWp;  // [9][Cout][Cin], pre-zeroed; accumulated with fp32 atomics (split-K over pixel tiles)
+  float* dWp;  // [9][Cout][Cin], pre-zeroed
+  float* db;   // [Cout], pre-zeroed, or null
   int N, H, W, Cin, Cout;
   int TW, TH, TN, tiles_w, tiles_h, tiles_n;
   int ksplit;
 };
 
-template <int BN>
-struct WgradCfg {
-  static constexpr int KP = 64;
-  static constexpr int STAGES = (BN == 128) ? 3 : 4;
-  static constexpr int A_BYTES = 4 * KP * 128;          // 4 co-blocks of [KP x 128 B]
-  static constexpr int B_BYTES = (BN / 32) * KP * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
-};
+constexpr int WG_KP = 64;                       // pixels per stage
+constexpr int WG_STAGES = 3;
+constexpr int WG_A_BYTES = 4 * WG_KP * 128;     // 4 co-blocks of [64 px x 128 B]            = 32 KB
+constexpr int WG_B_ONE = 96 * 128;              // one kw patch: (TH+2)*TW*TN = 96 rows      = 12 KB
+constexpr int WG_B_BYTES = 3 * WG_B_ONE;
+constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;   // 68 KB
+constexpr int WG_ONES_BYTES = 8 * 128;          // all-ones B tile: 8 k-rows x 128 B (reused for every k-step)
+constexpr int WG_BIAS_COL = 448;                 // TMEM column of the 128 x 16 bias-gradient accumulator (taps use 0..287)
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + WG_ONES_BYTES + 1024 + 256;
 
-template <int BN>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, WgradArgs a) {
-  using Cfg = WgradCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty = full + Cfg::STAGES;
-  uint64_t* accf = empty + Cfg::STAGES;
+  uint8_t* sB = smem + WG_STAGES * WG_A_BYTES;
+  float* ones = reinterpret_cast<float*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES + WG_ONES_BYTES);
+  uint64_t* empty = full + WG_STAGES;
+  uint64_t* accf = empty + WG_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_ci_tiles = a.Cin / BN;
-  int t = blockIdx.x;
-  const int ci_t = t % n_ci_tiles; t /= n_ci_tiles;
-  const int co_t = t;
-  const int tap = blockIdx.y;
-  const int kh = tap / 3, kw = tap - kh * 3;
-  const int split = blockIdx.z;
-  const int co0 = co_t * 128, ci0 = ci_t * BN;
+  const int n_ci_tiles = a.Cin / 32;
+  const int ci_t = blockIdx.x % n_ci_tiles, co_t = blockIdx.x / n_ci_tiles;
+  const int split = blockIdx.y;
+  const int co0 = co_t * 128, ci0 = ci_t * 32;
+  const bool do_bias = (a.db != nullptr) && (ci_t == 0);
   const long long total_tiles = (long long)a.tiles_w * a.tiles_h * a.tiles_n;
   const long long per = (total_tiles + a.ksplit - 1) / a.ksplit;
   const long long t_begin = per * split;
   const long long t_end = (t_begin + per < total_tiles) ? t_begin + per : total_tiles;
   const int nk = (int)(t_end > t_begin ? t_end - t_begin : 0);
+  const int img_rows = a.TH * a.TW;                 // A rows per image in the tile
+  const int patch_rows = (a.TH + 2) * a.TW;         // B rows per image in the patch
+  const int ksteps_img = img_rows / 8;
 
+  for (int i = threadIdx.x; i < WG_ONES_BYTES / 4; i += blockDim.x) ones[i] = 1.f;
+  fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmDY);
     tma_prefetch_desc(&tmX);
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(accf, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -306,37 +314,49 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
     if (warp == 0) {
       if (lane == 0) {
         for (int kb = 0; kb < nk; ++kb) {
-          const int s = kb % Cfg::STAGES;
-          const uint32_t ph = (kb / Cfg::STAGES) & 1;
+          const int s = kb % WG_STAGES;
+          const uint32_t ph = (kb / WG_STAGES) & 1;
           long long tt = t_begin + kb;
           const int tw = tt % a.tiles_w; tt /= a.tiles_w;
           const int th = tt % a.tiles_h; tt /= a.tiles_h;
           const int w0 = tw * a.TW, h0 = th * a.TH, n0 = (int)tt * a.TN;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-          uint8_t* pa = sA + s * Cfg::A_BYTES;
-          uint8_t* pb = sB + s * Cfg::B_BYTES;
+          mbar_expect_tx(&full[s], WG_A_BYTES + 3 * patch_rows * a.TN * 128);
+          uint8_t* pa = sA + s * WG_A_BYTES;
+          uint8_t* pb = sB + s * WG_B_BYTES;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_4d(pa + j * Cfg::KP * 128, &tmDY, &full[s], co0 + j * 32, w0, h0, n0);
+          for (int j = 0; j < 4; ++j) tma_load_4d(pa + j * WG_KP * 128, &tmDY, &full[s], co0 + j * 32, w0, h0, n0);
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j)
-            tma_load_4d(pb + j * Cfg::KP * 128, &tmX, &full[s], ci0 + j * 32, w0 + kw - 1, h0 + kh - 1, n0);
+          for (int kw = 0; kw < 3; ++kw) tma_load_4d(pb + kw * WG_B_ONE, &tmX, &full[s], ci0, w0 + kw - 1, h0 - 1, n0);
         }
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        const uint32_t idesc = make_idesc_tf32(128, BN, 1, 1);
+        const uint32_t idesc = make_idesc_tf32(128, 96, 1, 1);
+        const uint32_t idesc_b = make_idesc_tf32(128, 16, 1, 1);
+        const uint64_t ones_desc = make_sdesc_mn(smem_u32(ones), 0);
         for (int kb = 0; kb < nk; ++kb) {
-          const int s = kb % Cfg::STAGES;
-          const uint32_t ph = (kb / Cfg::STAGES) & 1;
+          const int s = kb % WG_STAGES;
+          const uint32_t ph = (kb / WG_STAGES) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+          const uint32_t a_addr = smem_u32(sA + s * WG_A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + s * WG_B_BYTES);
+          int kstep = 0;
+          for (int n = 0; n < a.TN; ++n) {
+            for (int j = 0; j < ksteps_img; ++j, ++kstep) {
+              const uint32_t accum = (kb | kstep) ? 1u : 0u;
+              const uint64_t ad = make_sdesc_mn(a_addr + (uint32_t)(n * img_rows + j * 8) * 128, WG_KP * 128);
+              // one MMA per kh with N = 96: the three kw patches are three 32-wide N-blocks WG_B_ONE bytes apart (LBO),
+              // so D columns [kh*96 + kw*32, +32) = tap kh*3+kw.  3 MMA issues per k-step instead of 9.
 #pragma unroll
-          for (int ks = 0; ks < Cfg::KP / 8; ++ks)
-            umma_tf32_ss(tmem_base, make_sdesc_mn(a_addr + ks * 1024, Cfg::KP * 128),
-                         make_sdesc_mn(b_addr + ks * 1024, Cfg::KP * 128), idesc, (kb | ks) ? 1u : 0u);
+              for (int kh = 0; kh < 3; ++kh) {
+                const uint32_t boff = (uint32_t)(n * patch_rows + kh * a.TW + j * 8) * 128;
+                umma_tf32_ss(tmem_base + kh * 96, ad, make_sdesc_mn(b_addr + boff, WG_B_ONE), idesc, accum);
+              }
+              if (do_bias) umma_tf32_ss(tmem_base + WG_BIAS_COL, ad, ones_desc, idesc_b, accum);
+            }
+          }
           umma_commit(&empty[s]);
         }
         umma_commit(accf);
@@ -347,48 +367,52 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
       mbar_wait(accf, 0);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int tap = 0; tap < 9; ++tap) {
         float v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tap * 32, v);
         tmem_ld_wait();
         if (co < a.Cout) {
-          float* dst = a.dWp + ((size_t)tap * a.Cout + co) * a.Cin + ci0 + c * 32;
+          float* dst = a.dWp + ((size_t)tap * a.Cout + co) * a.Cin + ci0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
         }
+      }
+      if (do_bias) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + WG_BIAS_COL, v);
+        tmem_ld_wait();
+        if (co < a.Cout) atomicAdd(a.db + co, v[0]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-template <int BN>
-static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradArgs& a, cudaStream_t stream) {
-  using Cfg = WgradCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(wgrad<%d>): %s", BN, cudaGetErrorString(e));
-    attr_set = true;
-  }
-  dim3 grid(((a.Cout + 127) / 128) * (a.Cin / BN), 9, a.ksplit);
-  conv3x3_wgrad_kernel<BN><<<grid, 192, Cfg::SMEM, stream>>>(tmDY, tmX, a);
-  HK_LAUNCH_CHECK("conv3x3_wgrad_kernel");
-  return 0;
+// pixel tile for wgrad: TW in {4,8,16} (kh shifts must be whole 512 B swizzle atoms), TW*TH*TN = 64, TH*TW % 8 == 0
+static bool pick_wgrad_tile(int W, int H, int* TW, int* TH, int* TN) {
+  int tw = 0;
+  for (int c : {16, 8, 4}) if (W % c == 0) { tw = c; break; }
+  if (!tw) return false;
+  int th = 1;
+  while (th * 2 * tw <= 64 && H % (th * 2) == 0) th *= 2;
+  if ((th * tw) % 8 != 0) return false;
+  *TW = tw; *TH = th; *TN = 64 / (tw * th);
+  return true;
 }
 
-int conv3x3_wgrad(const float* x, const float* dy, float* dwp, int N, int H, int W, int Cin, int Cout,
+int conv3x3_wgrad(const float* x, const float* dy, float* dwp, float* db, int N, int H, int W, int Cin, int Cout,
                   cudaStream_t stream) {
   HK_REQUIRE(x && dy && dwp, HK_ERR_ARG, "conv3x3_wgrad: null pointer");
-  HK_REQUIRE(Cin % 64 == 0 && Cout % 32 == 0, HK_ERR_UNSUPPORTED, "conv3x3_wgrad: Cin=%d Cout=%d unsupported", Cin, Cout);
+  HK_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0, HK_ERR_UNSUPPORTED, "conv3x3_wgrad: Cin=%d Cout=%d unsupported", Cin, Cout);
   WgradArgs a = {};
-  a.dWp = dwp; a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
-  pick_tile(W, H, N, 64, &a.TW, &a.TH, &a.TN);
+  a.dWp = dwp; a.db = db; a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
+  HK_REQUIRE(pick_wgrad_tile(W, H, &a.TW, &a.TH, &a.TN), HK_ERR_UNSUPPORTED,
+             "conv3x3_wgrad: W=%d must be a multiple of 4 and H=%d even", W, H);
+  HK_REQUIRE((a.TH + 2) * a.TW * a.TN * 128 <= WG_B_ONE, HK_ERR_UNSUPPORTED, "conv3x3_wgrad: halo patch too large");
   a.tiles_w = (W + a.TW - 1) / a.TW; a.tiles_h = (H + a.TH - 1) / a.TH; a.tiles_n = (N + a.TN - 1) / a.TN;
-  const int BN = (Cin % 128 == 0) ? 128 : 64;
-  const long long out_tiles = (long long)((Cout + 127) / 128) * (Cin / BN) * 9;
+  const long long out_tiles = (long long)((Cout + 127) / 128) * (Cin / 32);
   const long long total_tiles = (long long)a.tiles_w * a.tiles_h * a.tiles_n;
   long long ks = (148 * 2 + out_tiles - 1) / out_tiles;
   if (ks > total_tiles) ks = total_tiles;
@@ -398,122 +422,71 @@ int conv3x3_wgrad(const float* x, const float* dy, float* dwp, int N, int H, int
   CUtensorMap tmDY, tmX;
   int r;
   if ((r = make_act_map(&tmDY, dy, N, H, W, Cout, a.TW, a.TH, a.TN, true))) return r;
-  if ((r = make_act_map(&tmX, x, N, H, W, Cin, a.TW, a.TH, a.TN, true))) return r;
+  if ((r = make_act_map(&tmX, x, N, H, W, Cin, a.TW, a.TH + 2, a.TN, true))) return r;
   cudaError_t e = cudaMemsetAsync(dwp, 0, (size_t)9 * Cout * Cin * sizeof(float), stream);
   if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(dWp): %s", cudaGetErrorString(e));
-  if (BN == 128) return launch_wgrad<128>(tmDY, tmX, a, stream);
-  return launch_wgrad<64>(tmDY, tmX, a, stream);
+  if (db) {
+    e = cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), stream);
+    if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(db): %s", cudaGetErrorString(e));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)out_tiles, a.ksplit);
+  conv3x3_wgrad_kernel<<<grid, 192, WG_SMEM, stream>>>(tmDY, tmX, a);
+  HK_LAUNCH_CHECK("conv3x3_wgrad_kernel");
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// first layer (Cin = 3): direct fp32 conv, NCHW image in -> NHWC out, + bias + ReLU   (vgg.py:61, in_channels=3)
+// first layer (Cin = 3; vgg.py:61 in_channels=3): im2col to X27 + one tcgen05 GEMM (see hk_conv3x3_first_fwd)
 // ------------------------------------------------------------------------------------------------
-template <int COUT>
-__global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                            const float* __restrict__ bias, float* __restrict__ y,
-                                                            int N, int H, int W) {
-  __shared__ float sw[COUT * 27];
-  __shared__ float sb[COUT];
-  for (int i = threadIdx.x; i < COUT * 27; i += blockDim.x) {
-    // w [COUT][3][3][3] (co, ci, kh, kw) -> sw[(ci*9+kh*3+kw)*COUT + co]
-    const int co = i / 27, r = i % 27;
-    sw[r * COUT + co] = w[i];
-  }
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
-  __syncthreads();
-  // each thread: one pixel, 16 output channels (COUT/16 thread-groups share a pixel)
-  constexpr int G = COUT / 16;
-  const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long pix = gid / G;
-  const int g = (int)(gid % G);
+// first-layer weight gradient on the tensor cores: materialise the 3x3x3 patches as X27 [pix][32]
+// (27 taps, column 27 = 1.0 so that the GEMM's column 27 is the bias gradient, columns 28..31 = 0) and run
+// dW^T-partials[s] = dY[pix-range s]^T . X27[pix-range s]  as a batched (split-K) MN-major tcgen05 GEMM.
+__global__ void im2col_first_kernel(const float* __restrict__ x, float* __restrict__ x27, int N, int H, int W) {
   const long long total = (long long)N * H * W;
-  if (pix >= total) return;
-  const int wq = (int)(pix % W);
-  const int hq = (int)((pix / W) % H);
-  const int n = (int)(pix / ((long long)W * H));
-  float in[27];
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int wq = (int)(pix % W), hq = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+    float v[32];
 #pragma unroll
-  for (int ci = 0; ci < 3; ++ci)
+    for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
+      for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int hh = hq + kh - 1, ww = wq + kw - 1;
-        in[ci * 9 + kh * 3 + kw] =
-            (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(x + (((size_t)n * 3 + ci) * H + hh) * W + ww) : 0.f;
-      }
-  float acc[16];
+        for (int kw = 0; kw < 3; ++kw) {
+          const int hh = hq + kh - 1, ww = wq + kw - 1;
+          v[ci * 9 + kh * 3 + kw] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                                        ? tf32_round(__ldg(x + (((size_t)n * 3 + ci) * H + hh) * W + ww)) : 0.f;
+        }
+    v[27] = 1.f; v[28] = v[29] = v[30] = v[31] = 0.f;
+    float4* dst = reinterpret_cast<float4*>(x27 + (size_t)pix * 32);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = sb[g * 16 + j];
-#pragma unroll
-  for (int r = 0; r < 27; ++r) {
-    const float xv = in[r];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = fmaf(xv, sw[r * COUT + g * 16 + j], acc[j]);
+    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
-  float4* dst = reinterpret_cast<float4*>(y + (size_t)pix * COUT + g * 16);
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    dst[j] = make_float4(tf32_round(fmaxf(acc[4 * j], 0.f)), tf32_round(fmaxf(acc[4 * j + 1], 0.f)),
-                         tf32_round(fmaxf(acc[4 * j + 2], 0.f)), tf32_round(fmaxf(acc[4 * j + 3], 0.f)));
 }
-
-// first-layer weight gradient: dW[co][ci][kh][kw] = sum_pix dY[pix][co] * x[n][ci][h+kh-1][w+kw-1]; dY NHWC (already
-// ReLU-masked).  Block = 128 pixels x COUT; per-block partial sums reduced through shared memory, then atomics.
-template <int COUT>
-__global__ void __launch_bounds__(256) conv3x3_first_wgrad_kernel(const float* __restrict__ x,
-                                                                  const float* __restrict__ dy, float* __restrict__ dw,
-                                                                  int N, int H, int W, int pix_per_block) {
-  __shared__ float sx[64][28];      // 64 pixels x 27 taps (+pad)
-  __shared__ float sdy[64][COUT + 1];
-  const long long total = (long long)N * H * W;
-  const long long p_begin = (long long)blockIdx.x * pix_per_block;
-  const long long p_end = (p_begin + pix_per_block < total) ? p_begin + pix_per_block : total;
-  // thread -> (r, co-group): 27 taps x COUT outputs = 27*COUT accumulators over 256 threads
-  constexpr int PER = (27 * COUT + 255) / 256;
-  float acc[PER];
-#pragma unroll
-  for (int i = 0; i < PER; ++i) acc[i] = 0.f;
-  for (long long p0 = p_begin; p0 < p_end; p0 += 64) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 64 * 27; i += 256) {
-      const int pp = i / 27, r = i % 27;
-      const long long pix = p0 + pp;
-      float v = 0.f;
-      if (pix < p_end) {
-        const int wq = (int)(pix % W), hq = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
-        const int ci = r / 9, kh = (r % 9) / 3, kw = r % 3;
-        const int hh = hq + kh - 1, ww = wq + kw - 1;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + (((size_t)n * 3 + ci) * H + hh) * W + ww);
-      }
-      sx[pp][r] = v;
-    }
-    for (int i = threadIdx.x; i < 64 * COUT; i += 256) {
-      const int pp = i / COUT, co = i % COUT;
-      const long long pix = p0 + pp;
-      sdy[pp][co] = (pix < p_end) ? dy[(size_t)pix * COUT + co] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      const int idx = threadIdx.x + i * 256;
-      if (idx < 27 * COUT) {
-        const int co = idx % COUT, r = idx / COUT;
-        float s = 0.f;
-#pragma unroll 16
-        for (int pp = 0; pp < 64; ++pp) s = fmaf(sdy[pp][co], sx[pp][r], s);
-        acc[i] += s;
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    const int idx = threadIdx.x + i * 256;
-    if (idx < 27 * COUT) {
-      const int co = idx % COUT, r = idx / COUT;
-      atomicAdd(dw + (size_t)co * 27 + r, acc[i]);
-    }
-  }
+// w27[co][0..26] = tf32(w[co][ci][kh][kw]), w27[co][27] = bias[co] (x27 column 27 is 1.0), rest 0
+__global__ void pack_first_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                          float* __restrict__ w27, int Cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * 32) return;
+  const int co = i / 32, r = i % 32;
+  w27[i] = r < 27 ? tf32_round(w[co * 27 + r]) : (r == 27 && bias ? tf32_round(bias[co]) : 0.f);
+}
+// dw[co][r] = sum_s part[s][co][r] (r<27), db[co] = sum_s part[s][co][27]
+__global__ void first_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw,
+                                          float* __restrict__ db, int Cout, int S) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * 28) return;
+  const int co = i / 28, r = i % 28;
+  float s = 0.f;
+  for (int k = 0; k < S; ++k) s += part[((size_t)k * Cout + co) * 32 + r];
+  if (r < 27) dw[co * 27 + r] = s;
+  else if (db) db[co] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -638,55 +611,67 @@ int hk_conv3x3_wgrad(const float* x, const float* dy, float* dw, float* db, int 
   HK_REQUIRE(workspace && workspace_bytes >= hk_conv3x3_wgrad_workspace_bytes(Cin, Cout), HK_ERR_WORKSPACE,
              "hk_conv3x3_wgrad: workspace too small");
   float* dwp = static_cast<float*>(workspace);
-  int r = conv3x3_wgrad(x, dy, dwp, N, H, W, Cin, Cout, stream);
+  int r = conv3x3_wgrad(x, dy, dwp, db, N, H, W, Cin, Cout, stream);
   if (r) return r;
   unpack_wgrad_kernel<<<grid_for((size_t)Cout * Cin * 9, 256), 256, 0, stream>>>(dwp, dw, Cout, Cin);
   HK_LAUNCH_CHECK("unpack_wgrad_kernel");
-  if (db) {
-    cudaError_t e = cudaMemsetAsync(db, 0, Cout * sizeof(float), stream);
-    if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(db): %s", cudaGetErrorString(e));
-    const size_t npix = (size_t)N * H * W;
-    const int block = Cout >= 256 ? Cout : 256;
-    bias_grad_kernel<<<grid_for(npix, 64), block, 0, stream>>>(dy, db, npix, Cout);
-    HK_LAUNCH_CHECK("bias_grad_kernel");
-  }
   return 0;
 }
 
+size_t hk_conv3x3_first_fwd_workspace_bytes(int N, int H, int W, int Cout) {
+  return ((size_t)N * H * W * 32 + (size_t)Cout * 32) * sizeof(float);
+}
+
+/* y = relu(conv3x3(x) + bias) for the 3-channel input layer: patches are materialised once as X27 [pix][32]
+ * (tf32-rounded, column 27 = 1 carries the bias) and the layer is ONE tcgen05 GEMM  y = relu(X27 . W27^T).
+ * workspace = X27 followed by W27; X27 (the first N*H*W*32 floats) is what hk_conv3x3_first_wgrad consumes. */
 int hk_conv3x3_first_fwd(const float* x_nchw, const float* w, const float* bias, float* y_nhwc, int N, int H, int W,
-                         int Cout, void* stream) {
+                         int Cout, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
   HK_REQUIRE(x_nchw && w && y_nhwc, HK_ERR_ARG, "hk_conv3x3_first_fwd: null pointer");
-  HK_REQUIRE(Cout == 64 || Cout == 32 || Cout == 16, HK_ERR_UNSUPPORTED, "hk_conv3x3_first_fwd: Cout=%d unsupported", Cout);
-  const long long threads = (long long)N * H * W * (Cout / 16);
-  const int grid = (int)((threads + 255) / 256);
-  if (Cout == 64) conv3x3_first_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, w, bias, y_nhwc, N, H, W);
-  else if (Cout == 32) conv3x3_first_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, w, bias, y_nhwc, N, H, W);
-  else conv3x3_first_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, w, bias, y_nhwc, N, H, W);
-  HK_LAUNCH_CHECK("conv3x3_first_kernel");
-  return 0;
+  HK_REQUIRE(Cout % 4 == 0 && Cout <= 256, HK_ERR_UNSUPPORTED, "hk_conv3x3_first_fwd: Cout=%d unsupported", Cout);
+  HK_REQUIRE(workspace && workspace_bytes >= hk_conv3x3_first_fwd_workspace_bytes(N, H, W, Cout), HK_ERR_WORKSPACE,
+             "hk_conv3x3_first_fwd: workspace too small");
+  const long long P = (long long)N * H * W;
+  HK_REQUIRE(P < (1ll << 31), HK_ERR_UNSUPPORTED, "hk_conv3x3_first_fwd: too many pixels");
+  float* x27 = static_cast<float*>(workspace);
+  float* w27 = x27 + (size_t)P * 32;
+  im2col_first_kernel<<<grid_for((size_t)P, 128), 128, 0, stream>>>(x_nchw, x27, N, H, W);
+  HK_LAUNCH_CHECK("im2col_first_kernel");
+  pack_first_weights_kernel<<<(Cout * 32 + 127) / 128, 128, 0, stream>>>(w, bias, w27, Cout);
+  HK_LAUNCH_CHECK("pack_first_weights_kernel");
+  return hk_gemm_tf32(x27, 0, 32, 0, w27, 0, 32, 0, y_nhwc, Cout, 0, 0, (int)P, Cout, 32, 1, 1.f, nullptr, 0.f, nullptr,
+                      0, 0, 0.f, nullptr, 3 /*relu + tf32 round*/, stream_);
 }
 
-int hk_conv3x3_first_wgrad(const float* x_nchw, const float* dy_nhwc, float* dw, float* db, int N, int H, int W,
-                           int Cout, void* stream_) {
+static int first_wgrad_splits(long long P) {
+  for (int S = 592; S > 1; --S)
+    if (P % S == 0) return S;
+  return 1;
+}
+
+size_t hk_conv3x3_first_wgrad_workspace_bytes(int N, int H, int W, int Cout) {
+  return (size_t)first_wgrad_splits((long long)N * H * W) * Cout * 32 * sizeof(float);
+}
+
+/* dw [Cout,3,3,3], db [Cout] of the input layer from X27 (written by hk_conv3x3_first_fwd) and dy (ReLU-masked):
+ * split-K batched MN-major tcgen05 GEMM  partial[s] = dY_s^T . X27_s ; column 27 of the result is the bias grad. */
+int hk_conv3x3_first_wgrad(const float* x27, const float* dy_nhwc, float* dw, float* db, int N, int H, int W,
+                           int Cout, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  HK_REQUIRE(x_nchw && dy_nhwc && dw, HK_ERR_ARG, "hk_conv3x3_first_wgrad: null pointer");
-  HK_REQUIRE(Cout == 64 || Cout == 32 || Cout == 16, HK_ERR_UNSUPPORTED, "hk_conv3x3_first_wgrad: Cout=%d unsupported", Cout);
-  cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)Cout * 27 * sizeof(float), stream);
-  if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(dw): %s", cudaGetErrorString(e));
-  const long long total = (long long)N * H * W;
-  long long ppb = (total + 148 * 8 - 1) / (148 * 8);
-  ppb = ((ppb + 63) / 64) * 64;
-  const int grid = (int)((total + ppb - 1) / ppb);
-  if (Cout == 64) conv3x3_first_wgrad_kernel<64><<<grid, 256, 0, stream>>>(x_nchw, dy_nhwc, dw, N, H, W, (int)ppb);
-  else if (Cout == 32) conv3x3_first_wgrad_kernel<32><<<grid, 256, 0, stream>>>(x_nchw, dy_nhwc, dw, N, H, W, (int)ppb);
-  else conv3x3_first_wgrad_kernel<16><<<grid, 256, 0, stream>>>(x_nchw, dy_nhwc, dw, N, H, W, (int)ppb);
-  HK_LAUNCH_CHECK("conv3x3_first_wgrad_kernel");
-  if (db) {
-    e = cudaMemsetAsync(db, 0, Cout * sizeof(float), stream);
-    if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(db): %s", cudaGetErrorString(e));
-    bias_grad_kernel<<<grid_for((size_t)total, 64), 256, 0, stream>>>(dy_nhwc, db, (size_t)total, Cout);
-    HK_LAUNCH_CHECK("bias_grad_kernel");
-  }
+  HK_REQUIRE(x27 && dy_nhwc && dw, HK_ERR_ARG, "hk_conv3x3_first_wgrad: null pointer");
+  HK_REQUIRE(Cout % 4 == 0 && Cout <= 128, HK_ERR_UNSUPPORTED, "hk_conv3x3_first_wgrad: Cout=%d unsupported", Cout);
+  HK_REQUIRE(workspace && workspace_bytes >= hk_conv3x3_first_wgrad_workspace_bytes(N, H, W, Cout), HK_ERR_WORKSPACE,
+             "hk_conv3x3_first_wgrad: workspace too small");
+  const long long P = (long long)N * H * W;
+  const int S = first_wgrad_splits(P);
+  const long long Kc = P / S;
+  float* part = static_cast<float*>(workspace);
+  int r = hk_gemm_tf32(dy_nhwc, 1, Cout, Kc * Cout, x27, 1, 32, Kc * 32, part, 32, (long long)Cout * 32, 0, Cout, 32,
+                       (int)Kc, S, 1.f, nullptr, 0.f, nullptr, 0, 0, 0.f, nullptr, 0, stream_);
+  if (r) return r;
+  first_wgrad_reduce_kernel<<<(Cout * 28 + 127) / 128, 128, 0, stream>>>(part, dw, db, Cout, S);
+  HK_LAUNCH_CHECK("first_wgrad_reduce_kernel");
   return 0;
 }
 

@@ -141,7 +141,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float o = alpha * v[j];
           if (col == row) o += epi.diag;
           if (Db && col < N) o += beta * Db[(long long)row * epi.ldd + col];
-          if (epi.relu) o = fmaxf(o, 0.f);
+          if (epi.relu & 1) o = fmaxf(o, 0.f);
+          if (epi.relu & 2) o = tf32_round(o);   // output feeds another tf32 MMA: keep its error unbiased
           v[j] = o;
         }
         if (!epi.trans_c) {

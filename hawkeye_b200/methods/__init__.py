@@ -1,1 +1,2 @@
 from .bcnn import BCNN, BilinearPooling  # noqa: F401
+from .cbcnn import CBCNN, CompactBilinearPooling  # noqa: F401

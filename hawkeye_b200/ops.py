@@ -169,8 +169,9 @@ class VGGFeaturesFn(Function):
                 w, b = _f32c(params[2 * li]), params[2 * li + 1]
                 y = torch.empty(N, H, W, cout, device=dev, dtype=torch.float32)
                 if li == 0:
-                    _lib.call('hk_conv3x3_first_fwd', x, w, b, y, N, H, W, cout, s)
-                    rec = dict(kind='conv0', inp=None, out=y, H=H, W=W, cin=3, cout=cout)
+                    ws0 = _ws(_lib.query('hk_conv3x3_first_fwd_workspace_bytes', N, H, W, cout), dev)
+                    _lib.call('hk_conv3x3_first_fwd', x, w, b, y, N, H, W, cout, ws0, ws0.numel(), s)
+                    rec = dict(kind='conv0', inp=None, out=y, H=H, W=W, cin=3, cout=cout, x27=ws0 if save else None)
                 else:
                     wf = torch.empty(9 * cout * C, device=dev, dtype=torch.float32)
                     wd = torch.empty(9 * cout * C, device=dev, dtype=torch.float32) if save else None
@@ -219,7 +220,8 @@ class VGGFeaturesFn(Function):
             dw = torch.empty(cout, cin, 3, 3, device=dev, dtype=torch.float32)
             db = torch.empty(cout, device=dev, dtype=torch.float32)
             if rec['kind'] == 'conv0':
-                _lib.call('hk_conv3x3_first_wgrad', ctx.x, g, dw, db, N, H, W, cout, s)
+                ws = _ws(_lib.query('hk_conv3x3_first_wgrad_workspace_bytes', N, H, W, cout), dev)
+                _lib.call('hk_conv3x3_first_wgrad', rec['x27'], g, dw, db, N, H, W, cout, ws, ws.numel(), s)
             else:
                 ws = _ws(_lib.query('hk_conv3x3_wgrad_workspace_bytes', cin, cout), dev)
                 _lib.call('hk_conv3x3_wgrad', rec['inp'], g, dw, db, N, H, W, cin, cout, ws, ws.numel(), s)
@@ -267,3 +269,42 @@ def gemm_tf32(A, B, a_mn=False, b_mn=False, M=None, N=None, K=None, alpha=1.0, d
               int(trans_c), M, N, K, batch, float(alpha), alpha_vec, float(diag), D, ldd, sD, float(beta), beta_vec,
               int(relu), _lib.stream_ptr())
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CBCNN compact bilinear pooling (reference model/methods/CBCNN.py:38-164)
+# ----------------------------------------------------------------------------------------------------------
+def count_sketch_hashes(input_dim, output_dim):
+    """(h1, s1, h2, s2) int64 numpy arrays, bit-identical to CBCNN.py:76-91 (numpy legacy MT19937, seeds 1/3/5/7;
+    ``RandomState(seed)`` is the same stream as ``np.random.seed(seed)`` without clobbering the global RNG)."""
+    import numpy as np
+    h1 = np.random.RandomState(1).randint(output_dim, size=input_dim)
+    s1 = 2 * np.random.RandomState(3).randint(2, size=input_dim) - 1
+    h2 = np.random.RandomState(5).randint(output_dim, size=input_dim)
+    s2 = 2 * np.random.RandomState(7).randint(2, size=input_dim) - 1
+    return h1.astype(np.int64), s1.astype(np.int64), h2.astype(np.int64), s2.astype(np.int64)
+
+
+class CompactBilinearPoolFn(Function):
+    @staticmethod
+    def forward(ctx, x, h1, h2, s1, s2, d):
+        _check_cuda(x, h1, h2, s1, s2)
+        x = _f32c(x)
+        B, C, H, W = x.shape
+        y = torch.empty(B, d, device=x.device, dtype=torch.float32)
+        pre = torch.empty(B, d, device=x.device, dtype=torch.float32)
+        _lib.call('hk_cbp_fwd', x, h1, h2, s1, s2, y, pre, B, C, H * W, d, _lib.stream_ptr())
+        ctx.save_for_backward(x, pre, h1, h2, s1, s2)
+        ctx.d = d
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, pre, h1, h2, s1, s2 = ctx.saved_tensors
+        B, C, H, W = x.shape
+        d = ctx.d
+        dx = torch.empty_like(x)
+        ws = _ws(_lib.query('hk_cbp_bwd_workspace_bytes', B, C, d), x.device)
+        _lib.call('hk_cbp_bwd', x, pre, _f32c(dy), h1, h2, s1, s2, dx, B, C, H * W, d, ws, ws.numel(),
+                  _lib.stream_ptr())
+        return dx, None, None, None, None, None

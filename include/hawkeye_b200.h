@@ -45,6 +45,17 @@ size_t hk_bilinear_pool_bwd_workspace_bytes(int B, int C, int HW);
 int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int C, int HW, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* ---- CBCNN compact bilinear pooling: model/methods/CBCNN.py:96-135 (CompactBilinearPooling.forward) ------------
+ * h1,h2 int32 [C] and s1,s2 fp32 [C] are the count-sketch hash / sign vectors of CBCNN.py:76-91 (numpy seeds 1/3/5/7,
+ * generated bit-exactly on the host).  y [B,d] = normalize(signed_sqrt(tensor-sketch)); pre [B,d] (pre-sqrt sketch)
+ * is saved for the backward.  Requires C%128==0, HW%4==0. */
+int hk_cbp_fwd(const float* x, const int* h1, const int* h2, const float* s1, const float* s2, float* y, float* pre,
+               int B, int C, int HW, int d, void* stream);
+size_t hk_cbp_bwd_workspace_bytes(int B, int C, int d);
+int hk_cbp_bwd(const float* x, const float* pre, const float* dy, const int* h1, const int* h2, const float* s1,
+               const float* s2, float* dx, int B, int C, int HW, int d, void* workspace, size_t workspace_bytes,
+               void* stream);
+
 /* ---- VGG-16 backbone: model/backbone/vgg.py:56-70 (Conv2d 3x3 s1 p1 + bias, ReLU, MaxPool2d(2,2)) ----------
  * Activations are NHWC fp32 inside the backbone.  Weights keep the reference layout [Cout,Cin,3,3] in the
  * state_dict and are re-packed per step: w_fwd [9][Cout][Cin], w_dgrad [9][Cin][Cout] (taps flipped). */
@@ -55,15 +66,18 @@ int hk_conv3x3_fwd(const float* x_nhwc, const float* w_fwd_packed, const float* 
 /* dx = conv3x3^T(dy, w) * (relu_mask_act > 0)  (mask optional: the ReLU output that produced x) */
 int hk_conv3x3_dgrad(const float* dy_nhwc, const float* w_dgrad_packed, const float* relu_mask_act, float* dx_nhwc,
                      int N, int H, int W, int Cin, int Cout, void* stream);
-/* dw [Cout,Cin,3,3] (reference layout), db [Cout] (optional) from x, dy (dy already ReLU-masked).  Cin%64==0. */
+/* dw [Cout,Cin,3,3] (reference layout), db [Cout] (optional) from x, dy (dy already ReLU-masked).  Cin%32==0, W%4==0. */
 size_t hk_conv3x3_wgrad_workspace_bytes(int Cin, int Cout);
 int hk_conv3x3_wgrad(const float* x_nhwc, const float* dy_nhwc, float* dw, float* db, int N, int H, int W, int Cin,
                      int Cout, void* workspace, size_t workspace_bytes, void* stream);
-/* first layer (Cin=3): NCHW image in, NHWC out, bias+ReLU fused; and its weight/bias gradient */
+/* first layer (Cin=3, vgg.py:61): NCHW image in, NHWC out, bias+ReLU fused.  The 3x3x3 patches are materialised once
+ * as X27 [N*H*W][32] (start of the fwd workspace) and reused by the weight/bias gradient. */
+size_t hk_conv3x3_first_fwd_workspace_bytes(int N, int H, int W, int Cout);
 int hk_conv3x3_first_fwd(const float* x_nchw, const float* w, const float* bias, float* y_nhwc, int N, int H, int W,
-                         int Cout, void* stream);
-int hk_conv3x3_first_wgrad(const float* x_nchw, const float* dy_nhwc, float* dw, float* db, int N, int H, int W,
-                           int Cout, void* stream);
+                         int Cout, void* workspace, size_t workspace_bytes, void* stream);
+size_t hk_conv3x3_first_wgrad_workspace_bytes(int N, int H, int W, int Cout);
+int hk_conv3x3_first_wgrad(const float* x27, const float* dy_nhwc, float* dw, float* db, int N, int H, int W,
+                           int Cout, void* workspace, size_t workspace_bytes, void* stream);
 /* MaxPool2d(2,2) on NHWC; out_nchw=1 writes the pooled map as NCHW (input of the pooling heads).
  * bwd routes dy to the first max (PyTorch semantics) and multiplies by (x>0), i.e. also applies the ReLU backward. */
 int hk_maxpool2x2_fwd(const float* x_nhwc, float* y, int N, int H, int W, int C, int out_nchw, void* stream);

@@ -62,7 +62,7 @@ def test_conv3x3_fwd_dgrad_wgrad(N, H, W, Cin, Cout):
     _lib.call('hk_conv3x3_wgrad', xg, dpre_g, dw, db, N, H, W, Cin, Cout, ws, nb, s)
     ew, eb = rel_l2(dw.cpu(), gw), rel_l2(db.cpu(), gb)
     print(f'conv wgrad: {ew:.2e} bias {eb:.2e}')
-    assert ew < TOL and eb < 1e-4
+    assert ew < TOL and eb < 1e-3   # bias grad comes out of the same tf32 MMA (ones column)
 
 
 def test_first_layer_and_pool():
@@ -75,15 +75,21 @@ def test_first_layer_and_pool():
     xd, wd_, bd = x.double(), w.double().requires_grad_(True), b.double().requires_grad_(True)
     y_ref = F.relu(F.conv2d(xd, wd_, bd, padding=1))
     y = torch.empty(N, H, W, Cout, device='cuda')
-    _lib.call('hk_conv3x3_first_fwd', x.cuda(), w.cuda(), b.cuda(), y, N, H, W, Cout, s)
+    nb0 = _lib.query('hk_conv3x3_first_fwd_workspace_bytes', N, H, W, Cout)
+    ws0 = torch.empty(nb0, dtype=torch.uint8, device='cuda')
+    _lib.call('hk_conv3x3_first_fwd', x.cuda(), w.cuda(), b.cuda(), y, N, H, W, Cout, ws0, nb0, s)
+    print('first fwd', rel_l2(_nchw(y).cpu(), y_ref.detach()))
     assert rel_l2(_nchw(y).cpu(), y_ref.detach()) < 1e-3   # fp32 math, tf32-rounded on store
     dy = detgen.det((N, Cout, H, W), 4).double()
     gw, gb = torch.autograd.grad(y_ref, (wd_, bd), dy)
     dpre = _nhwc((dy * (y_ref > 0)).float()).cuda()
     dw = torch.empty(Cout, 3, 3, 3, device='cuda')
     db = torch.empty(Cout, device='cuda')
-    _lib.call('hk_conv3x3_first_wgrad', x.cuda(), dpre, dw, db, N, H, W, Cout, s)
-    assert rel_l2(dw.cpu(), gw) < 1e-4 and rel_l2(db.cpu(), gb) < 1e-4
+    nb = _lib.query('hk_conv3x3_first_wgrad_workspace_bytes', N, H, W, Cout)
+    ws = torch.empty(nb, dtype=torch.uint8, device='cuda')
+    _lib.call('hk_conv3x3_first_wgrad', ws0, dpre, dw, db, N, H, W, Cout, ws, nb, s)
+    print('first wgrad', rel_l2(dw.cpu(), gw), rel_l2(db.cpu(), gb))
+    assert rel_l2(dw.cpu(), gw) < 2e-3 and rel_l2(db.cpu(), gb) < 2e-3
     # max-pool fwd (NHWC and NCHW-out) and bwd (first-max routing + ReLU mask)
     a = F.relu(detgen.det((N, 64, H, W), 7)).double().requires_grad_(True)
     p_ref = F.max_pool2d(a, 2, 2)
