@@ -8,6 +8,8 @@
 //   fwd   : Y[pix, co]  = sum_{tap,ci} X[pix+tap, ci] * Wf[tap][co][ci]        (+bias, ReLU)
 //   dgrad : dX[pix, ci] = sum_{tap,co} dY[pix+tap, co] * Wd[tap][ci][co]       (Wd = flipped/transposed W; * (act>0))
 //   wgrad : dW[tap][co][ci] = sum_pix dY[pix, co] * X[pix+tap, ci]             (both operands MN-major; split-K)
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host.h"
 #include "../../include/hawkeye_b200.h"
@@ -256,6 +258,7 @@ struct WgradArgs {
   int N, H, W, Cin, Cout;
   int TW, TH, TN, tiles_w, tiles_h, tiles_n;
   int ksplit;
+  int dbg;
 };
 
 constexpr int WG_KP = 64;                       // pixels per stage
@@ -349,12 +352,24 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
               const uint64_t ad = make_sdesc_mn(a_addr + (uint32_t)(n * img_rows + j * 8) * 128, WG_KP * 128);
               // one MMA per kh with N = 96: the three kw patches are three 32-wide N-blocks WG_B_ONE bytes apart (LBO),
               // so D columns [kh*96 + kw*32, +32) = tap kh*3+kw.  3 MMA issues per k-step instead of 9.
+              if (do_bias && a.dbg == 1) umma_tf32_ss(tmem_base + WG_BIAS_COL, ad, ones_desc, idesc_b, accum);
+              if (a.dbg == 4) {
+                for (int tap = 0; tap < 9; ++tap) {
+                  const int kh = tap / 3, kw = tap - kh * 3;
+                  const uint32_t boff = (uint32_t)(n * patch_rows + kh * a.TW + j * 8) * 128;
+                  umma_tf32_ss(tmem_base + tap * 32, ad, make_sdesc_mn(b_addr + kw * WG_B_ONE + boff, 0),
+                               make_idesc_tf32(128, 32, 1, 1), accum);
+                }
+              } else {
 #pragma unroll
-              for (int kh = 0; kh < 3; ++kh) {
-                const uint32_t boff = (uint32_t)(n * patch_rows + kh * a.TW + j * 8) * 128;
-                umma_tf32_ss(tmem_base + kh * 96, ad, make_sdesc_mn(b_addr + boff, WG_B_ONE), idesc, accum);
+                for (int kh = 0; kh < 3; ++kh) {
+                  const uint32_t boff = (uint32_t)(n * patch_rows + kh * a.TW + j * 8) * 128;
+                  umma_tf32_ss(tmem_base + kh * 96, ad, make_sdesc_mn(b_addr + boff, WG_B_ONE), idesc, accum);
+                }
               }
-              if (do_bias) umma_tf32_ss(tmem_base + WG_BIAS_COL, ad, ones_desc, idesc_b, accum);
+              if (do_bias && a.dbg != 1)
+                umma_tf32_ss(tmem_base + WG_BIAS_COL, ad, ones_desc, a.dbg == 2 ? make_idesc_tf32(128, 32, 1, 1) : idesc_b,
+                             accum);
             }
           }
           umma_commit(&empty[s]);
@@ -419,6 +434,7 @@ int conv3x3_wgrad(const float* x, const float* dy, float* dwp, float* db, int N,
   if (ks < 1) ks = 1;
   if (ks > 65535) ks = 65535;
   a.ksplit = (int)ks;
+  { const char* v = getenv("HK_DBG_WG"); a.dbg = v ? atoi(v) : 0; }
   CUtensorMap tmDY, tmX;
   int r;
   if ((r = make_act_map(&tmDY, dy, N, H, W, Cout, a.TW, a.TH, a.TN, true))) return r;

@@ -61,7 +61,7 @@ def test_conv3x3_fwd_dgrad_wgrad(N, H, W, Cin, Cout):
     ws = torch.empty(nb, dtype=torch.uint8, device='cuda')
     _lib.call('hk_conv3x3_wgrad', xg, dpre_g, dw, db, N, H, W, Cin, Cout, ws, nb, s)
     ew, eb = rel_l2(dw.cpu(), gw), rel_l2(db.cpu(), gb)
-    print(f'conv wgrad: {ew:.2e} bias {eb:.2e}')
+    print(f'conv wgrad: {ew:.2e} bias {eb:.2e}', (db.cpu().double()[:4] / gb[:4]).tolist(), gb[:4].tolist())
     assert ew < TOL and eb < 1e-3   # bias grad comes out of the same tf32 MMA (ones column)
 
 
