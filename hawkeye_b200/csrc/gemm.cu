@@ -12,21 +12,11 @@
 
 #include "common.cuh"
 #include "host.h"
+#include "gemm.h"
 #include "../../include/hawkeye_b200.h"
 
 namespace hk {
 
-struct GemmEpi {
-  float* C;
-  long long ldc, strideC;
-  const float* D;
-  long long ldd, strideD;
-  const float* alpha_vec;
-  const float* beta_vec;
-  float alpha, beta, diag;
-  int trans_c;
-  int relu;
-};
 
 template <int BN>
 struct GemmCfg {
@@ -128,6 +118,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const float beta = epi.beta * (epi.beta_vec ? epi.beta_vec[bz] : 1.f);
     float* Cb = epi.C + (long long)bz * epi.strideC;
     const float* Db = epi.D ? epi.D + (long long)bz * epi.strideD : nullptr;
+    const float* Dlb = (epi.D && epi.D_lo) ? epi.D_lo + (long long)bz * epi.strideD : nullptr;
+    const float* Eb = epi.E ? epi.E + (long long)bz * epi.strideC : nullptr;
+    float* Clb = epi.C_lo ? epi.C_lo + (long long)bz * epi.strideC : nullptr;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
@@ -138,14 +131,29 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = col0 + j;
-          float o = alpha * v[j];
+          float acc = v[j];
+          if (Eb && col < N) acc += Eb[(long long)row * epi.ldc + col];
+          float o = alpha * acc;
           if (col == row) o += epi.diag;
-          if (Db && col < N) o += beta * Db[(long long)row * epi.ldd + col];
+          if (Db && col < N) {
+            float dv = Db[(long long)row * epi.ldd + col];
+            if (Dlb) dv += Dlb[(long long)row * epi.ldd + col];
+            o += beta * dv;
+          }
           if (epi.relu & 1) o = fmaxf(o, 0.f);
           if (epi.relu & 2) o = tf32_round(o);   // output feeds another tf32 MMA: keep its error unbiased
           v[j] = o;
         }
-        if (!epi.trans_c) {
+        if (Clb) {   // (hi, lo) split store; not combined with trans_c
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float hi = tf32_round(v[j]);
+            if (col0 + j < N) {
+              Cb[(long long)row * epi.ldc + col0 + j] = hi;
+              Clb[(long long)row * epi.ldc + col0 + j] = tf32_round(v[j] - hi);
+            }
+          }
+        } else if (!epi.trans_c) {
           float* dst = Cb + (long long)row * epi.ldc + col0;
           if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
@@ -237,6 +245,7 @@ extern "C" int hk_gemm_tf32(const float* A, int a_mn_major, long long lda, long 
   epi.alpha_vec = alpha_vec; epi.beta_vec = beta_vec;
   epi.alpha = alpha; epi.beta = beta; epi.diag = diag;
   epi.trans_c = trans_c; epi.relu = relu;
+  epi.C_lo = nullptr; epi.D_lo = nullptr; epi.E = nullptr;
   return hk::gemm_tf32(A, a_mn_major, lda, strideA, B, b_mn_major, ldb, strideB, epi, M, N, K, batch,
                        static_cast<cudaStream_t>(stream));
 }

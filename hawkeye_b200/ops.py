@@ -308,3 +308,89 @@ class CompactBilinearPoolFn(Function):
         _lib.call('hk_cbp_bwd', x, pre, _f32c(dy), h1, h2, s1, s2, dx, B, C, H * W, d, ws, ws.numel(),
                   _lib.stream_ptr())
         return dx, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Fast MPN-COV pooling head (reference model/methods/MPNCOV.py:105-242)
+# ----------------------------------------------------------------------------------------------------------
+class CovpoolFn(Function):
+    """Covpool (MPNCOV.py:105-134): [B,C,H,W] -> [B,C,C]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _check_cuda(x)
+        x = _f32c(x)
+        B, C, H, W = x.shape
+        cov = torch.empty(B, C, C, device=x.device, dtype=torch.float32)
+        xc = torch.empty(B, C, H * W, device=x.device, dtype=torch.float32)
+        _lib.call('hk_covpool_fwd', x, cov, xc, B, C, H * W, _lib.stream_ptr())
+        ctx.save_for_backward(xc)
+        ctx.shape = x.shape
+        return cov
+
+    @staticmethod
+    def backward(ctx, g):
+        (xc,) = ctx.saved_tensors
+        B, C, H, W = ctx.shape
+        dx = torch.empty(B, C, H, W, device=g.device, dtype=torch.float32)
+        _lib.call('hk_covpool_bwd', xc, _f32c(g), dx, B, C, H * W, _lib.stream_ptr())
+        return dx
+
+
+class SqrtmFn(Function):
+    """Sqrtm (MPNCOV.py:137-202): coupled Newton-Schulz forward + the reference's own backward recurrence."""
+
+    @staticmethod
+    def forward(ctx, x, iterN):
+        _check_cuda(x)
+        x = _f32c(x)
+        B, n, _ = x.shape
+        y = torch.empty_like(x)
+        saved = torch.empty(_lib.query('hk_sqrtm_saved_floats', B, n, iterN), device=x.device, dtype=torch.float32)
+        ws = _ws(_lib.query('hk_sqrtm_fwd_workspace_bytes', B, n), x.device)
+        _lib.call('hk_sqrtm_fwd', x, y, saved, B, n, iterN, ws, ws.numel(), _lib.stream_ptr())
+        ctx.save_for_backward(x, y, saved)
+        ctx.iterN = iterN
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, saved = ctx.saved_tensors
+        B, n, _ = x.shape
+        gx = torch.empty_like(x)
+        ws = _ws(_lib.query('hk_sqrtm_bwd_workspace_bytes', B, n), x.device)
+        _lib.call('hk_sqrtm_bwd', x, y, _f32c(g), saved, gx, B, n, ctx.iterN, ws, ws.numel(), _lib.stream_ptr())
+        return gx, None
+
+
+class TriuvecFn(Function):
+    """Triuvec (MPNCOV.py:205-230): [B,n,n] -> [B, n(n+1)/2, 1]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _check_cuda(x)
+        x = _f32c(x)
+        B, n, _ = x.shape
+        y = torch.empty(B, n * (n + 1) // 2, 1, device=x.device, dtype=torch.float32)
+        _lib.call('hk_triuvec_fwd', x, y, B, n, _lib.stream_ptr())
+        ctx.n = n
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        B, n = g.shape[0], ctx.n
+        dx = torch.empty(B, n, n, device=g.device, dtype=torch.float32)
+        _lib.call('hk_triuvec_bwd', _f32c(g), dx, B, n, _lib.stream_ptr())
+        return dx
+
+
+def CovpoolLayer(var):
+    return CovpoolFn.apply(var)
+
+
+def SqrtmLayer(var, iterN):
+    return SqrtmFn.apply(var, iterN)
+
+
+def TriuvecLayer(var):
+    return TriuvecFn.apply(var)

@@ -56,6 +56,23 @@ int hk_cbp_bwd(const float* x, const float* pre, const float* dy, const int* h1,
                const float* s2, float* dx, int B, int C, int HW, int d, void* workspace, size_t workspace_bytes,
                void* stream);
 
+/* ---- Fast MPN-COV pooling head: model/methods/MPNCOV.py:105-230 -----------------------------------------------
+ * Covpool (:105-134): x [B,C,M] -> cov [B,C,C] = X I_hat X^T; xc [B,C,M] receives the centred features (saved for bwd).
+ * Sqrtm (:137-202): coupled Newton-Schulz, iterN >= 2, forward and the reference's hand-derived backward formulae,
+ *   all products as 3xTF32 tcgen05 GEMMs.  `saved` (hk_sqrtm_saved_floats floats) carries A, Y_i, Z_i, normA.
+ * Triuvec (:205-230): row-major upper triangle [B,n,n] <-> [B,n(n+1)/2]. */
+int hk_covpool_fwd(const float* x, float* cov, float* xc, int B, int C, int M, void* stream);
+int hk_covpool_bwd(const float* xc, const float* g, float* dx, int B, int C, int M, void* stream);
+size_t hk_sqrtm_saved_floats(int B, int n, int iterN);
+size_t hk_sqrtm_fwd_workspace_bytes(int B, int n);
+size_t hk_sqrtm_bwd_workspace_bytes(int B, int n);
+int hk_sqrtm_fwd(const float* x, float* y, float* saved, int B, int n, int iterN, void* workspace,
+                 size_t workspace_bytes, void* stream);
+int hk_sqrtm_bwd(const float* x, const float* y, const float* g, float* saved, float* grad_x, int B, int n, int iterN,
+                 void* workspace, size_t workspace_bytes, void* stream);
+int hk_triuvec_fwd(const float* x, float* y, int B, int n, void* stream);
+int hk_triuvec_bwd(const float* g, float* dx, int B, int n, void* stream);
+
 /* ---- VGG-16 backbone: model/backbone/vgg.py:56-70 (Conv2d 3x3 s1 p1 + bias, ReLU, MaxPool2d(2,2)) ----------
  * Activations are NHWC fp32 inside the backbone.  Weights keep the reference layout [Cout,Cin,3,3] in the
  * state_dict and are re-packed per step: w_fwd [9][Cout][Cin], w_dgrad [9][Cin][Cout] (taps flipped). */
