@@ -28,17 +28,17 @@ struct GemmCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, (BN == 64 ? 3 : (BN == 128 ? 2 : 1)))
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpi epi, int M,
-                 int N, int K, int a_mn, int b_mn, int shareA, int shareB, int mn_sbo, int mn_type) {
+                 int N, int K, int a_mn, int b_mn, int shareA, int shareB, int mn_sbo, int mn_type, int nstages) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty = full + Cfg::STAGES;
-  uint64_t* accf = empty + Cfg::STAGES;
+  uint8_t* sB = smem + nstages * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + nstages * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + nstages;
+  uint64_t* accf = empty + nstages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -48,7 +48,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    for (int s = 0; s < nstages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -68,8 +68,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       const int bza = shareA ? 0 : bz, bzb = shareB ? 0 : bz;
       for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        const int s = kb % nstages;
+        const uint32_t ph = (kb / nstages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
         uint8_t* a = sA + s * Cfg::A_BYTES;
@@ -92,8 +92,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(128, BN, a_mn, b_mn);
       for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        const int s = kb % nstages;
+        const uint32_t ph = (kb / nstages) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
@@ -212,7 +212,13 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     attr_set = true;
   }
   dim3 grid((M + 127) / 128, (N + BN - 1) / BN, batch);
-  umma_gemm_kernel<BN><<<grid, 192, Cfg::SMEM, stream>>>(tmA, tmB, epi, M, N, K, a_mn, b_mn, shareA, shareB, dbg_env("HK_DBG_MN_SBO", 512), dbg_env("HK_DBG_MN_TYPE", 1));
+  // short-K problems (e.g. the K=32 first-layer GEMM) take only the pipeline stages they can use, so several CTAs
+  // fit per SM and their prologues/epilogues overlap
+  const int nk = (K + 31) / 32;
+  const int nstages = nk < Cfg::STAGES ? nk : Cfg::STAGES;
+  const int smem = nstages * Cfg::STAGE_BYTES + 1024 + 256;
+  umma_gemm_kernel<BN><<<grid, 192, smem, stream>>>(tmA, tmB, epi, M, N, K, a_mn, b_mn, shareA, shareB,
+                                                    dbg_env("HK_DBG_MN_SBO", 512), dbg_env("HK_DBG_MN_TYPE", 1), nstages);
   HK_LAUNCH_CHECK("umma_gemm_kernel");
   return 0;
 }

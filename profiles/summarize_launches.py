@@ -20,7 +20,7 @@ def load(path):
 
 def main(path):
     seq = load(path)
-    starts = [i for i, (n, _) in enumerate(seq) if 'conv3x3_first_kernel' in n]
+    starts = [i for i, (n, _) in enumerate(seq) if 'im2col_first_kernel' in n or 'conv3x3_first_kernel' in n]
     ends = [i for i, (n, _) in enumerate(seq) if 'sgd_momentum_kernel' in n or 'adam_kernel' in n]
     if starts and ends and ends[-1] > starts[-1]:
         seq = seq[starts[-1]:ends[-1] + 1]
