@@ -91,49 +91,53 @@ struct GramArgs {
   int d;
 };
 
-constexpr int GRAM_STAGES = 3;
+constexpr int GRAM_STAGES = 6;
 constexpr int GRAM_SLOT = 128 * 128;              // 16 KB: 128 rows x 32 fp32
 constexpr int GRAM_STAGE_BYTES = 2 * GRAM_SLOT;   // two row blocks per stage
-constexpr int GRAM_SMEM = GRAM_STAGES * GRAM_STAGE_BYTES + 1024 + 256;
+constexpr int GRAM_SMEM = GRAM_STAGES * GRAM_STAGE_BYTES + 1024 + 512;
+constexpr int GRAM_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
+// decode work item t of an image into its two 128-row blocks
+__device__ __forceinline__ void gram_item(int t, int nblk, int& blk0, int& blk1, int& diag) {
+  const int n_off = nblk * (nblk - 1) / 2;
+  if (t < n_off) {
+    diag = 0;
+    int i = 0;
+    while (t >= nblk - 1 - i) { t -= nblk - 1 - i; ++i; }
+    blk0 = i; blk1 = i + 1 + t;
+  } else {
+    diag = 1;
+    blk0 = 2 * (t - n_off);
+    blk1 = (blk0 + 1 < nblk) ? blk0 + 1 : -1;
+  }
+}
+
+// Persistent: one CTA per SM walks items it, it+grid, ...  (item = image * items_per_image + pair).  The smem ring (6 stages)
+// and the two TMEM accumulator sets (2 x 256 columns) run across item boundaries, so the epilogue of item i (8 warps)
+// overlaps the TMA/MMA of item i+1.
 template <int MODE>
-__global__ void __launch_bounds__(192, 2) gram_pair_kernel(const __grid_constant__ CUtensorMap tmX, GramArgs a) {
+__global__ void __launch_bounds__(GRAM_THREADS, 1) gram_pair_kernel(const __grid_constant__ CUtensorMap tmX, GramArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + GRAM_STAGES * GRAM_STAGE_BYTES);
   uint64_t* empty = full + GRAM_STAGES;
-  uint64_t* accf = empty + GRAM_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
-  float* red = reinterpret_cast<float*>(tmem_slot + 1);  // 4 floats + 1 result
+  uint64_t* acc_full = empty + GRAM_STAGES;    // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* red = reinterpret_cast<float*>(tmem_slot + 2);  // 8 partial sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y;
-  // ---- decode the work item into two row blocks
-  const int n_off = a.nblk * (a.nblk - 1) / 2;
-  int blk0, blk1, diag;
-  {
-    int t = blockIdx.x;
-    if (t < n_off) {
-      diag = 0;
-      int i = 0;
-      while (t >= a.nblk - 1 - i) { t -= a.nblk - 1 - i; ++i; }
-      blk0 = i; blk1 = i + 1 + t;
-    } else {
-      diag = 1;
-      blk0 = 2 * (t - n_off);
-      blk1 = (blk0 + 1 < a.nblk) ? blk0 + 1 : -1;
-    }
-  }
-  const int nacc = (blk1 >= 0) ? 2 : 1;
+  const int ipi = a.nblk * (a.nblk - 1) / 2 + (a.nblk + 1) / 2;   // items per image
+  const int total_items = a.B * ipi;
   const int nk = (a.HW + 31) / 32;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     for (int s = 0; s < GRAM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(accf, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -141,125 +145,161 @@ __global__ void __launch_bounds__(192, 2) gram_pair_kernel(const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % GRAM_STAGES;
-        const uint32_t ph = (kb / GRAM_STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], nacc * GRAM_SLOT);
-        uint8_t* st = smem + s * GRAM_STAGE_BYTES;
-        tma_load_3d(st, &tmX, &full[s], kb * 32, blk0 * 128, b);
-        if (blk1 >= 0) tma_load_3d(st + GRAM_SLOT, &tmX, &full[s], kb * 32, blk1 * 128, b);
+      uint64_t policy;   // keep X resident in L2: every row block is re-read by several CTAs while Y streams through
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+      int kbg = 0;
+      for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+        const int b = it / ipi;
+        int blk0, blk1, diag;
+        gram_item(it - b * ipi, a.nblk, blk0, blk1, diag);
+        for (int kb = 0; kb < nk; ++kb, ++kbg) {
+          const int s = kbg % GRAM_STAGES;
+          const uint32_t ph = (kbg / GRAM_STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], (blk1 >= 0 ? 2 : 1) * GRAM_SLOT);
+          uint8_t* st = smem + s * GRAM_STAGE_BYTES;
+          tma_load_3d_hint(st, &tmX, &full[s], kb * 32, blk0 * 128, b, policy);
+          if (blk1 >= 0) tma_load_3d_hint(st + GRAM_SLOT, &tmX, &full[s], kb * 32, blk1 * 128, b, policy);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(128, 128, 0, 0);
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % GRAM_STAGES;
-        const uint32_t ph = (kb / GRAM_STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      int kbg = 0, itl = 0;
+      for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++itl) {
+        const int b = it / ipi;
+        int blk0, blk1, diag;
+        gram_item(it - b * ipi, a.nblk, blk0, blk1, diag);
+        const int set = itl & 1;
+        mbar_wait(&acc_empty[set], ((itl >> 1) & 1) ^ 1);     // epilogue has drained this accumulator set
         tc_fence_after();
-        const uint32_t s0 = smem_u32(smem + s * GRAM_STAGE_BYTES);
-        const uint32_t s1 = s0 + GRAM_SLOT;
-        const int krem = a.HW - kb * 32;
-        const int ksteps = krem >= 32 ? 4 : (krem + 7) / 8;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t d0 = make_sdesc(s0 + ks * 32, 16, 1024);
-          const uint64_t d1 = make_sdesc(s1 + ks * 32, 16, 1024);
-          const uint32_t accum = (kb | ks) ? 1u : 0u;
-          if (diag) {
-            umma_tf32_ss(tmem_base, d0, d0, idesc, accum);
-            if (blk1 >= 0) umma_tf32_ss(tmem_base + 128, d1, d1, idesc, accum);
-          } else {
-            umma_tf32_ss(tmem_base, d0, d1, idesc, accum);        // acc0 = X_blk0 X_blk1^T
-            umma_tf32_ss(tmem_base + 128, d1, d0, idesc, accum);  // acc1 = X_blk1 X_blk0^T
+        const uint32_t d_base = tmem_base + set * 256;
+        for (int kb = 0; kb < nk; ++kb, ++kbg) {
+          const int s = kbg % GRAM_STAGES;
+          const uint32_t ph = (kbg / GRAM_STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t s0 = smem_u32(smem + s * GRAM_STAGE_BYTES);
+          const uint32_t s1 = s0 + GRAM_SLOT;
+          const int krem = a.HW - kb * 32;
+          const int ksteps = krem >= 32 ? 4 : (krem + 7) / 8;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t d0 = make_sdesc(s0 + ks * 32, 16, 1024);
+            const uint64_t d1 = make_sdesc(s1 + ks * 32, 16, 1024);
+            const uint32_t accum = (kb | ks) ? 1u : 0u;
+            if (diag) {
+              umma_tf32_ss(d_base, d0, d0, idesc, accum);
+              if (blk1 >= 0) umma_tf32_ss(d_base + 128, d1, d1, idesc, accum);
+            } else {
+              umma_tf32_ss(d_base, d0, d1, idesc, accum);        // acc0 = X_blk0 X_blk1^T
+              umma_tf32_ss(d_base + 128, d1, d0, idesc, accum);  // acc1 = X_blk1 X_blk0^T
+            }
           }
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        umma_commit(&acc_full[set]);
       }
-      umma_commit(accf);
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps (128 threads)
+    // ------------------------------------------------------------ epilogue: 8 warps; warp w reads TMEM lane quarter w%4,
+    // columns [half*64, half*64+64) of each 128-column accumulator
     const int q = warp & 3;
-    const int et = threadIdx.x - 64;  // 0..127
-    float inv_norm = 1.f;
-    if (MODE == MODE_BCNN_FWD) {
-      // closed-form norm from the channel-sum partials (K0 may still be running: wait for it here, not at launch)
-      asm volatile("griddepcontrol.wait;" ::: "memory");
-      float acc = 0.f;
-      const float* pb = a.partial + (size_t)b * a.CS * a.HW;
-      for (int p = et; p < a.HW; p += 128) {
-        float s = 0.f;
-        for (int cs = 0; cs < a.CS; ++cs) s += pb[cs * a.HW + p];
-        acc = fmaf(s, s, acc);
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) red[q] = acc;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const float tot = red[0] + red[1] + red[2] + red[3];
-      const float nrm = sqrtf(tot * a.inv_hw + (float)a.C * (float)a.C * a.eps);
-      inv_norm = 1.f / fmaxf(nrm, 1e-12f);
-      if (blockIdx.x == 0 && et == 0 && a.inv_norm) a.inv_norm[b] = inv_norm;
-    }
-    mbar_wait(accf, 0);
-    tc_fence_after();
-    float craw = 0.f;
+    const int half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;  // 0..255
+    if (MODE == MODE_BCNN_FWD) asm volatile("griddepcontrol.wait;" ::: "memory");   // K0's channel sums
     const size_t CC = (size_t)a.C * a.C;
-    for (int ac = 0; ac < nacc; ++ac) {
-      int ablk, bblk;
-      if (diag) { ablk = bblk = (ac == 0 ? blk0 : blk1); }
-      else      { ablk = (ac == 0 ? blk0 : blk1); bblk = (ac == 0 ? blk1 : blk0); }
-      const int ia = ablk * 128 + q * 32 + lane;  // row of the A block held by this thread
+    int itl = 0, cur_b = -1;
+    float inv_norm = 1.f;
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++itl) {
+      const int b = it / ipi;
+      int blk0, blk1, diag;
+      gram_item(it - b * ipi, a.nblk, blk0, blk1, diag);
+      const int nacc = blk1 >= 0 ? 2 : 1;
+      if (MODE == MODE_BCNN_FWD && b != cur_b) {
+        // closed-form norm from the channel-sum partials (overlaps the TMA/MMA pipeline of this item)
+        cur_b = b;
+        float acc = 0.f;
+        const float* pb = a.partial + (size_t)b * a.CS * a.HW;
+        for (int p = et; p < a.HW; p += 256) {
+          float s = 0.f;
+          for (int cs = 0; cs < a.CS; ++cs) s += pb[cs * a.HW + p];
+          acc = fmaf(s, s, acc);
+        }
+        acc = warp_sum(acc);
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // previous item's readers of red[] are done
+        if (lane == 0) red[warp - 2] = acc;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += red[i];
+        const float nrm = sqrtf(tot * a.inv_hw + (float)a.C * (float)a.C * a.eps);
+        inv_norm = 1.f / fmaxf(nrm, 1e-12f);
+        if (it - b * ipi == 0 && et == 0 && a.inv_norm) a.inv_norm[b] = inv_norm;
+      }
+      const int set = itl & 1;
+      mbar_wait(&acc_full[set], (itl >> 1) & 1);
+      tc_fence_after();
+      float craw = 0.f;
+      for (int ac = 0; ac < nacc; ++ac) {
+        int ablk, bblk;
+        if (diag) { ablk = bblk = (ac == 0 ? blk0 : blk1); }
+        else      { ablk = (ac == 0 ? blk0 : blk1); bblk = (ac == 0 ? blk1 : blk0); }
+        const int ia = ablk * 128 + q * 32 + lane;  // row of the A block held by this thread
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ac * 128 + c * 32, v);
-        tmem_ld_wait();
-        const int jb0 = bblk * 128 + c * 32;
-        if (MODE == MODE_BCNN_FWD) {
-          float* y = a.Y + (size_t)b * CC + (size_t)jb0 * a.C + ia;
+        for (int c = half * 2; c < half * 2 + 2; ++c) {
+          float v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + set * 256 + ac * 128 + c * 32, v);
+          tmem_ld_wait();
+          const int jb0 = bblk * 128 + c * 32;
+          if (MODE == MODE_BCNN_FWD) {
+            float* y = a.Y + (size_t)b * CC + (size_t)jb0 * a.C + ia;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[(size_t)j * a.C] = tf32_round(fast_sqrt(fmaf(v[j], a.inv_hw, a.eps)) * inv_norm);
-        } else if (MODE == MODE_BCNN_BWD_S) {
-          const float* dyt = a.dY + (size_t)b * CC + (size_t)jb0 * a.C + ia;   // dY[jb][ia]: coalesced over lanes
-          const float4* dyd = reinterpret_cast<const float4*>(a.dY + (size_t)b * CC + (size_t)ia * a.C + jb0);
-          float* s = a.S + (size_t)b * CC + (size_t)jb0 * a.C + ia;
-          float dd[32], dtv[32];
+            for (int j = 0; j < 32; ++j)   // streaming store: Y is written once and must not evict X from L2
+              __stcs(y + (size_t)j * a.C, tf32_round(fast_sqrt(fmaf(v[j], a.inv_hw, a.eps)) * inv_norm));
+          } else if (MODE == MODE_BCNN_BWD_S) {
+            const float* dyt = a.dY + (size_t)b * CC + (size_t)jb0 * a.C + ia;   // dY[jb][ia]: coalesced over lanes
+            const float4* dyd = reinterpret_cast<const float4*>(a.dY + (size_t)b * CC + (size_t)ia * a.C + jb0);
+            float* s = a.S + (size_t)b * CC + (size_t)jb0 * a.C + ia;
+            float dd[32], dtv[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 t = __ldg(dyd + j);
-            dd[4 * j] = t.x; dd[4 * j + 1] = t.y; dd[4 * j + 2] = t.z; dd[4 * j + 3] = t.w;
-          }
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = __ldg(dyd + j);
+              dd[4 * j] = t.x; dd[4 * j + 1] = t.y; dd[4 * j + 2] = t.z; dd[4 * j + 3] = t.w;
+            }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dtv[j] = __ldg(dyt + (size_t)j * a.C);   // all loads in flight before any store
+            for (int j = 0; j < 32; ++j) dtv[j] = __ldg(dyt + (size_t)j * a.C);   // all loads in flight before any store
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float z = fast_sqrt(fmaf(v[j], a.inv_hw, a.eps));
-            craw = fmaf(dtv[j], z, craw);
-            s[(size_t)j * a.C] = tf32_round(__fdividef(dtv[j] + dd[j], 2.f * z));
-          }
-        } else {  // MODE_CBP_FWD: signed scatter of the raw Gram into the d sketch bins
-          const int hi = a.h1[ia];
-          const float si = a.s1[ia];
-          float* bins = a.bins + (size_t)b * a.d;
+            for (int j = 0; j < 32; ++j) {
+              const float z = fast_sqrt(fmaf(v[j], a.inv_hw, a.eps));
+              craw = fmaf(dtv[j], z, craw);
+              s[(size_t)j * a.C] = tf32_round(__fdividef(dtv[j] + dd[j], 2.f * z));
+            }
+          } else {  // MODE_CBP_FWD: signed scatter of the raw Gram into the d sketch bins
+            const int hi = a.h1[ia];
+            const float si = a.s1[ia];
+            float* bins = a.bins + (size_t)b * a.d;
 #pragma unroll 8
-          for (int j = 0; j < 32; ++j) {
-            int bin = hi + a.h2[jb0 + j];
-            if (bin >= a.d) bin -= a.d;
-            atomicAdd(&bins[bin], si * a.s2[jb0 + j] * v[j]);
+            for (int j = 0; j < 32; ++j) {
+              int bin = hi + a.h2[jb0 + j];
+              if (bin >= a.d) bin -= a.d;
+              atomicAdd(&bins[bin], si * a.s2[jb0 + j] * v[j]);
+            }
           }
         }
       }
-    }
-    if (MODE == MODE_BCNN_BWD_S) {
-      craw = warp_sum(craw);
-      if (lane == 0) atomicAdd(&a.c_raw[b], craw);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[set]);     // 8 warp arrivals free the accumulator set
+      if (MODE == MODE_BCNN_BWD_S) {
+        craw = warp_sum(craw);
+        if (lane == 0) atomicAdd(&a.c_raw[b], craw);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 static int make_x_map(CUtensorMap* tm, const float* X, int B, int C, int HW) {
@@ -267,6 +307,16 @@ static int make_x_map(CUtensorMap* tm, const float* X, int B, int C, int HW) {
   uint64_t strides[2] = {(uint64_t)HW * 4, (uint64_t)C * HW * 4};
   uint32_t box[3] = {32, 128, 1};
   return make_tmap(tm, X, 3, dims, strides, box);
+}
+
+static int gram_grid(int total_items) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return total_items < sms ? total_items : sms;
 }
 
 template <int MODE>
@@ -278,11 +328,12 @@ static int launch_gram(const CUtensorMap& tm, const GramArgs& a, cudaStream_t st
     attr_set = true;
   }
   const int items = a.nblk * (a.nblk - 1) / 2 + (a.nblk + 1) / 2;
+  const int grid = gram_grid(items * a.B);
   if (MODE == MODE_BCNN_FWD) {
     // programmatic dependent launch: overlap this kernel's prologue + TMA/MMA pipeline with the channel-sum kernel
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(items, a.B);
-    cfg.blockDim = dim3(192);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GRAM_THREADS);
     cfg.dynamicSmemBytes = GRAM_SMEM;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -293,7 +344,7 @@ static int launch_gram(const CUtensorMap& tm, const GramArgs& a, cudaStream_t st
     cudaError_t e = cudaLaunchKernelEx(&cfg, gram_pair_kernel<MODE>, tm, a);
     if (e != cudaSuccess) return set_error((int)e, "cudaLaunchKernelEx(gram): %s", cudaGetErrorString(e));
   } else {
-    gram_pair_kernel<MODE><<<dim3(items, a.B), 192, GRAM_SMEM, stream>>>(tm, a);
+    gram_pair_kernel<MODE><<<grid, GRAM_THREADS, GRAM_SMEM, stream>>>(tm, a);
   }
   HK_LAUNCH_CHECK("gram_pair_kernel");
   return 0;
