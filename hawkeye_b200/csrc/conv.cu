@@ -53,6 +53,7 @@ struct ConvArgs {
   int TW, TH, TN;      // pixel tile (product 128)
   int tiles_w, tiles_h, tiles_n;
   int relu;
+  int stride;          // 1 or 2 (N,H,W above are OUTPUT dims; the input map is H*stride x W*stride)
 };
 
 template <int BN>
@@ -109,7 +110,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const int kh = tap / 3, kw = tap - kh * 3;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-        tma_load_4d(sA + s * Cfg::A_BYTES, &tmX, &full[s], ck * 32, w0 + kw - 1, h0 + kh - 1, n0);
+        tma_load_4d(sA + s * Cfg::A_BYTES, &tmX, &full[s], ck * 32, w0 * a.stride + kw - 1, h0 * a.stride + kh - 1, n0);
         tma_load_3d(sB + s * Cfg::B_BYTES, &tmW, &full[s], ck * 32, co0, tap);
       }
     }
@@ -192,11 +193,13 @@ static void pick_tile(int W, int H, int N, int target, int* TW, int* TH, int* TN
 }
 
 static int make_act_map(CUtensorMap* tm, const float* X, int N, int H, int W, int C, int TW, int TH, int TN,
-                        bool mn_major = false) {
+                        bool mn_major = false, int stride = 1) {
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
   uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
-  uint32_t box[4] = {32, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
-  return make_tmap(tm, X, 4, dims, strides, box, mn_major);
+  // strided traversal: the box spans TW*stride elements and TMA keeps every stride-th one
+  uint32_t box[4] = {32, (uint32_t)(TW * stride), (uint32_t)(TH * stride), (uint32_t)TN};
+  uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+  return make_tmap(tm, X, 4, dims, strides, box, mn_major, stride > 1 ? estr : nullptr);
 }
 
 template <int BN>
@@ -216,7 +219,13 @@ static int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const Con
 
 // x NHWC [N,H,W,Cin], wp packed [9][Cout][Cin] -> y NHWC [N,H,W,Cout]
 int conv3x3_igemm(const float* x, const float* wp, const float* bias, const float* mask, float* y, int N, int H, int W,
-                  int Cin, int Cout, int relu, cudaStream_t stream) {
+                  int Cin, int Cout, int relu, cudaStream_t stream, int stride = 1) {
+  // H, W are the INPUT dims; output is H/stride x W/stride (padding 1)
+  const int Hin = H, Win = W;
+  if (stride == 2) {
+    HK_REQUIRE(H % 2 == 0 && W % 2 == 0, HK_ERR_UNSUPPORTED, "conv3x3 stride 2: even H/W required");
+    H /= 2; W /= 2;
+  }
   HK_REQUIRE(x && wp && y, HK_ERR_ARG, "conv3x3: null pointer");
   HK_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0, HK_ERR_UNSUPPORTED, "conv3x3: Cin=%d Cout=%d must be multiples of 32",
              Cin, Cout);
@@ -224,12 +233,13 @@ int conv3x3_igemm(const float* x, const float* wp, const float* bias, const floa
              "conv3x3: pointer not 16-byte aligned");
   ConvArgs a = {};
   a.Y = y; a.bias = bias; a.mask = mask; a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.relu = relu;
+  a.stride = stride;
   pick_tile(W, H, N, 128, &a.TW, &a.TH, &a.TN);
   a.tiles_w = (W + a.TW - 1) / a.TW; a.tiles_h = (H + a.TH - 1) / a.TH; a.tiles_n = (N + a.TN - 1) / a.TN;
   HK_REQUIRE((long long)a.tiles_w * a.tiles_h * a.tiles_n < (1ll << 31), HK_ERR_UNSUPPORTED, "conv3x3: grid too large");
   CUtensorMap tmX, tmW;
   int r;
-  if ((r = make_act_map(&tmX, x, N, H, W, Cin, a.TW, a.TH, a.TN))) return r;
+  if ((r = make_act_map(&tmX, x, N, Hin, Win, Cin, a.TW, a.TH, a.TN, false, stride))) return r;
   const int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
   {
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
@@ -409,11 +419,15 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
 static bool pick_wgrad_tile(int W, int H, int* TW, int* TH, int* TN) {
   int tw = 0;
   for (int c : {16, 8, 4}) if (W % c == 0) { tw = c; break; }
-  if (!tw) return false;
+  if (!tw) tw = W <= 4 ? 4 : (W <= 8 ? 8 : 16);   // over-wide tile: out-of-range columns are TMA zero fill
   int th = 1;
   while (th * 2 * tw <= 64 && H % (th * 2) == 0) th *= 2;
-  if ((th * tw) % 8 != 0) return false;
-  *TW = tw; *TH = th; *TN = 64 / (tw * th);
+  int tn = 64 / (tw * th);
+  if ((th * tw) % 8 != 0 || (th + 2) * tw * tn > 96) {   // fall back to one image per tile, partial tiles in H allowed
+    th = 64 / tw;
+    tn = 1;
+  }
+  *TW = tw; *TH = th; *TN = tn;
   return true;
 }
 
@@ -423,8 +437,7 @@ int conv3x3_wgrad(const float* x, const float* dy, float* dwp, float* db, int N,
   HK_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0, HK_ERR_UNSUPPORTED, "conv3x3_wgrad: Cin=%d Cout=%d unsupported", Cin, Cout);
   WgradArgs a = {};
   a.dWp = dwp; a.db = db; a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
-  HK_REQUIRE(pick_wgrad_tile(W, H, &a.TW, &a.TH, &a.TN), HK_ERR_UNSUPPORTED,
-             "conv3x3_wgrad: W=%d must be a multiple of 4 and H=%d even", W, H);
+  pick_wgrad_tile(W, H, &a.TW, &a.TH, &a.TN);
   HK_REQUIRE((a.TH + 2) * a.TW * a.TN * 128 <= WG_B_ONE, HK_ERR_UNSUPPORTED, "conv3x3_wgrad: halo patch too large");
   a.tiles_w = (W + a.TW - 1) / a.TW; a.tiles_h = (H + a.TH - 1) / a.TH; a.tiles_n = (N + a.TN - 1) / a.TN;
   const long long out_tiles = (long long)((Cout + 127) / 128) * (Cin / 32);
@@ -613,6 +626,11 @@ int hk_conv3x3_pack_weights(const float* w, float* w_fwd, float* w_dgrad, int Co
 int hk_conv3x3_fwd(const float* x, const float* w_packed, const float* bias, float* y, int N, int H, int W, int Cin,
                    int Cout, int relu, void* stream) {
   return conv3x3_igemm(x, w_packed, bias, nullptr, y, N, H, W, Cin, Cout, relu, (cudaStream_t)stream);
+}
+
+int hk_conv3x3_s2_fwd(const float* x, const float* w_packed, const float* bias, float* y, int N, int H, int W, int Cin,
+                      int Cout, int relu, void* stream) {
+  return conv3x3_igemm(x, w_packed, bias, nullptr, y, N, H, W, Cin, Cout, relu, (cudaStream_t)stream, 2);
 }
 
 int hk_conv3x3_dgrad(const float* dy, const float* w_dgrad_packed, const float* relu_mask_act, float* dx, int N, int H,

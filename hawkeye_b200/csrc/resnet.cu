@@ -1,0 +1,478 @@
+// Support kernels of the ResNet-50 v1.5 trunk (reference model/backbone/resnet.py:89-252) around the tensor-core
+// convolutions: 7x7/s2 stem patch extraction, train-mode BatchNorm2d (batch statistics, running-stat update,
+// fused residual add + ReLU) forward/backward, MaxPool2d(3,2,1), stride-2 sub/up-sampling, 1x1-conv weight
+// gradient (split-K GEMM).  All activations NHWC fp32; every kernel here is HBM-bound.
+#include "common.cuh"
+#include "host.h"
+#include "gemm.h"
+#include "../../include/hawkeye_b200.h"
+
+namespace hk {
+
+static inline int rgrid(size_t n, int block) {
+  size_t g = (n + block - 1) / block;
+  const size_t cap = 148 * 16;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------------ stem (resnet.py:176)
+// X147[pix][ci*49 + kh*7 + kw] = x[n][ci][2*ho+kh-3][2*wo+kw-3] (0 outside), columns 147..159 = 0; tf32-rounded
+__global__ void stem_im2col_kernel(const float* __restrict__ x, float* __restrict__ o, int N, int H, int W, int Ho,
+                                   int Wo) {
+  const long long total = (long long)N * Ho * Wo * 40;   // 40 float4 per pixel
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % 40);
+    const long long pix = i / 40;
+    const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = q * 4 + e;
+      float t = 0.f;
+      if (col < 147) {
+        const int ci = col / 49, r = col % 49, kh = r / 7, kw = r % 7;
+        const int hh = 2 * ho + kh - 3, ww = 2 * wo + kw - 3;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) t = tf32_round(__ldg(x + (((size_t)n * 3 + ci) * H + hh) * W + ww));
+      }
+      v[e] = t;
+    }
+    reinterpret_cast<float4*>(o)[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+__global__ void pack_stem_weights_kernel(const float* __restrict__ w, float* __restrict__ o, int Cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * 160) return;
+  const int co = i / 160, c = i % 160;
+  o[i] = c < 147 ? tf32_round(w[co * 147 + c]) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------ BatchNorm2d (train)
+// per-block partial column sums of x and x^2 over a slab of pixels:  part[blk][0][c], part[blk][1][c]
+__global__ void bn_stats_partial_kernel(const float* __restrict__ x, float* __restrict__ part, long long P, int C) {
+  extern __shared__ float sm[];   // [2][plan][C4*4]
+  const int C4 = C / 4;
+  const int clanes = C4 < (int)blockDim.x ? C4 : (int)blockDim.x;
+  const int plan = (int)blockDim.x / clanes;
+  const int cl = threadIdx.x % clanes, pl = threadIdx.x / clanes;
+  const long long per = (P + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per, p1 = (p0 + per < P) ? p0 + per : P;
+  for (int c4 = cl; c4 < C4; c4 += clanes) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    if (pl < plan) {
+#pragma unroll 4
+      for (long long p = p0 + pl; p < p1; p += plan) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * C) + c4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+      }
+      reinterpret_cast<float4*>(sm + (size_t)pl * C)[c4] = s;
+      reinterpret_cast<float4*>(sm + (size_t)(plan + pl) * C)[c4] = q;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < plan; ++k) { s += sm[(size_t)k * C + c]; q += sm[(size_t)(plan + k) * C + c]; }
+    part[((size_t)blockIdx.x * 2) * C + c] = s;
+    part[((size_t)blockIdx.x * 2 + 1) * C + c] = q;
+  }
+}
+// mean / invstd (biased variance) + running-stat update with the unbiased variance (nn.BatchNorm2d, momentum 0.1)
+__global__ void bn_stats_finalize_kernel(const float* __restrict__ part, int nblk, long long P, int C, float eps,
+                                         float momentum, float* __restrict__ mean, float* __restrict__ invstd,
+                                         float* __restrict__ rmean, float* __restrict__ rvar) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblk; ++b) { s += part[((size_t)b * 2) * C + c]; q += part[((size_t)b * 2 + 1) * C + c]; }
+  const double m = s / (double)P;
+  double var = q / (double)P - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (rmean) {
+    const double unb = P > 1 ? var * (double)P / (double)(P - 1) : var;
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)m;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+  }
+}
+// y = [relu]( (x-mean)*invstd*gamma + beta [+ residual] ), tf32-rounded (it feeds the next MMA)
+__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const float* __restrict__ res, float* __restrict__ y,
+                                size_t total4, int C4, int relu) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float4 m = reinterpret_cast<const float4*>(mean)[c4], is = reinterpret_cast<const float4*>(invstd)[c4];
+    const float4 g = reinterpret_cast<const float4*>(gamma)[c4], b = reinterpret_cast<const float4*>(beta)[c4];
+    float4 o;
+    o.x = fmaf((v.x - m.x) * is.x, g.x, b.x); o.y = fmaf((v.y - m.y) * is.y, g.y, b.y);
+    o.z = fmaf((v.z - m.z) * is.z, g.z, b.z); o.w = fmaf((v.w - m.w) * is.w, g.w, b.w);
+    if (res) {
+      const float4 r = reinterpret_cast<const float4*>(res)[i];
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    reinterpret_cast<float4*>(y)[i] = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
+  }
+}
+// backward reductions: part[blk][0][c] = sum dy', part[blk][1][c] = sum dy' * xhat,  dy' = dy * (y > 0 if relu)
+__global__ void bn_bwd_partial_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                      const float* __restrict__ dy, const float* __restrict__ mean,
+                                      const float* __restrict__ invstd, float* __restrict__ part, long long P, int C,
+                                      int relu) {
+  extern __shared__ float sm[];
+  const int C4 = C / 4;
+  const int clanes = C4 < (int)blockDim.x ? C4 : (int)blockDim.x;
+  const int plan = (int)blockDim.x / clanes;
+  const int cl = threadIdx.x % clanes, pl = threadIdx.x / clanes;
+  const long long per = (P + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per, p1 = (p0 + per < P) ? p0 + per : P;
+  for (int c4 = cl; c4 < C4; c4 += clanes) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    if (pl < plan) {
+      const float4 m = reinterpret_cast<const float4*>(mean)[c4], is = reinterpret_cast<const float4*>(invstd)[c4];
+#pragma unroll 2
+      for (long long p = p0 + pl; p < p1; p += plan) {
+        float4 g = __ldg(reinterpret_cast<const float4*>(dy + p * C) + c4);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * C) + c4);
+        if (relu) {
+          const float4 o = __ldg(reinterpret_cast<const float4*>(y + p * C) + c4);
+          g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+        }
+        s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+        q.x = fmaf(g.x, (v.x - m.x) * is.x, q.x); q.y = fmaf(g.y, (v.y - m.y) * is.y, q.y);
+        q.z = fmaf(g.z, (v.z - m.z) * is.z, q.z); q.w = fmaf(g.w, (v.w - m.w) * is.w, q.w);
+      }
+      reinterpret_cast<float4*>(sm + (size_t)pl * C)[c4] = s;
+      reinterpret_cast<float4*>(sm + (size_t)(plan + pl) * C)[c4] = q;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < plan; ++k) { s += sm[(size_t)k * C + c]; q += sm[(size_t)(plan + k) * C + c]; }
+    part[((size_t)blockIdx.x * 2) * C + c] = s;
+    part[((size_t)blockIdx.x * 2 + 1) * C + c] = q;
+  }
+}
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblk; ++b) { s += part[((size_t)b * 2) * C + c]; q += part[((size_t)b * 2 + 1) * C + c]; }
+  dbeta[c] = (float)s;
+  dgamma[c] = (float)q;
+}
+// dx = gamma*invstd*(dy' - dbeta/P - xhat*dgamma/P)  (tf32-rounded: operand of dgrad/wgrad);  dres = dy' (optional)
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                    const float* __restrict__ dy, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                                    float* __restrict__ dx, float* __restrict__ dres, size_t total4, int C4, float invP,
+                                    int relu) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    float4 g = reinterpret_cast<const float4*>(dy)[i];
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    if (relu) {
+      const float4 o = reinterpret_cast<const float4*>(y)[i];
+      g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+    }
+    if (dres) reinterpret_cast<float4*>(dres)[i] = g;
+    const float4 m = reinterpret_cast<const float4*>(mean)[c4], is = reinterpret_cast<const float4*>(invstd)[c4];
+    const float4 ga = reinterpret_cast<const float4*>(gamma)[c4];
+    const float4 dg = reinterpret_cast<const float4*>(dgamma)[c4], db = reinterpret_cast<const float4*>(dbeta)[c4];
+    float4 o;
+    o.x = ga.x * is.x * (g.x - db.x * invP - (v.x - m.x) * is.x * dg.x * invP);
+    o.y = ga.y * is.y * (g.y - db.y * invP - (v.y - m.y) * is.y * dg.y * invP);
+    o.z = ga.z * is.z * (g.z - db.z * invP - (v.z - m.z) * is.z * dg.z * invP);
+    o.w = ga.w * is.w * (g.w - db.w * invP - (v.w - m.w) * is.w * dg.w * invP);
+    reinterpret_cast<float4*>(dx)[i] = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ MaxPool2d(3, 2, 1)
+__global__ void maxpool3x3s2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C,
+                                        int Ho, int Wo) {
+  const int C4 = C / 4;
+  const size_t total = (size_t)N * Ho * Wo * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = i % C4;
+    size_t p = i / C4;
+    const int wo = p % Wo; p /= Wo;
+    const int ho = p % Ho;
+    const int n = p / Ho;
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hh = 2 * ho + kh - 1;
+      if (hh < 0 || hh >= H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ww = 2 * wo + kw - 1;
+        if (ww < 0 || ww >= W) continue;
+        const float4 v = reinterpret_cast<const float4*>(x + (((size_t)n * H + hh) * W + ww) * C)[c4];
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    reinterpret_cast<float4*>(y)[i] = m;
+  }
+}
+// gather form: dx[pixel] = sum over the (<=4) windows containing it of dy[window] if this pixel is that window's
+// first maximum (PyTorch routing).  No atomics; x is the pool input, y its output.
+__global__ void maxpool3x3s2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                        const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W,
+                                        int C, int Ho, int Wo) {
+  const size_t total = (size_t)N * H * W * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    size_t p = i / C;
+    const int w = p % W; p /= W;
+    const int h = p % H;
+    const int n = p / H;
+    const float v = x[i];
+    float g = 0.f;
+    for (int ho = (h + 1) / 2 - ((h + 1) % 2 == 0 ? 1 : 0); ho <= (h + 1) / 2; ++ho) {
+      if (ho < 0 || ho >= Ho) continue;
+      for (int wo = (w + 1) / 2 - ((w + 1) % 2 == 0 ? 1 : 0); wo <= (w + 1) / 2; ++wo) {
+        if (wo < 0 || wo >= Wo) continue;
+        const size_t oi = (((size_t)n * Ho + ho) * Wo + wo) * C + c;
+        if (y[oi] != v) continue;
+        // first maximum in scan order inside window (ho, wo)?
+        bool first = true;
+        for (int kh = 0; kh < 3 && first; ++kh) {
+          const int hh = 2 * ho + kh - 1;
+          if (hh < 0 || hh >= H) continue;
+          for (int kw = 0; kw < 3; ++kw) {
+            const int ww = 2 * wo + kw - 1;
+            if (ww < 0 || ww >= W) continue;
+            if (hh == h && ww == w) { kh = 3; break; }
+            if (x[(((size_t)n * H + hh) * W + ww) * C + c] == v) { first = false; break; }
+          }
+        }
+        if (first) g += dy[oi];
+      }
+    }
+    dx[i] = g;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ stride-2 helpers
+__global__ void subsample2_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C4) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const size_t total = (size_t)N * Ho * Wo * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = i % C4;
+    size_t p = i / C4;
+    const int wo = p % Wo; p /= Wo;
+    const int ho = p % Ho;
+    const int n = p / Ho;
+    reinterpret_cast<float4*>(y)[i] = reinterpret_cast<const float4*>(x)[(((size_t)n * H + 2 * ho) * W + 2 * wo) * C4 + c4];
+  }
+}
+// x[n][h][w] = (h,w even) ? y[n][h/2][w/2] : 0
+__global__ void upsample2_zero_kernel(const float* __restrict__ y, float* __restrict__ x, int N, int H, int W, int C4) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const size_t total = (size_t)N * H * W * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = i % C4;
+    size_t p = i / C4;
+    const int w = p % W; p /= W;
+    const int h = p % H;
+    const int n = p / H;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (((h | w) & 1) == 0) v = reinterpret_cast<const float4*>(y)[(((size_t)n * Ho + h / 2) * Wo + w / 2) * C4 + c4];
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+}
+__global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 u = reinterpret_cast<float4*>(a)[i];
+    const float4 v = reinterpret_cast<const float4*>(b)[i];
+    u.x += v.x; u.y += v.y; u.z += v.z; u.w += v.w;
+    reinterpret_cast<float4*>(a)[i] = u;
+  }
+}
+// out[i] = sum_s part[s][i]
+__global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, size_t n, int S) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < S; ++k) s += part[(size_t)k * n + i];
+    out[i] = s;
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int HW, int C) {
+  const size_t total = (size_t)N * HW * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int p = i % HW;
+    const int c = (i / HW) % C;
+    const int n = i / ((size_t)HW * C);
+    y[i] = x[((size_t)n * HW + p) * C + c];
+  }
+}
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int HW, int C) {
+  const size_t total = (size_t)N * HW * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const int p = (i / C) % HW;
+    const int n = i / ((size_t)HW * C);
+    y[i] = x[((size_t)n * C + c) * HW + p];
+  }
+}
+
+static int bn_blocks(long long P) {
+  long long b = (P + 255) / 256;
+  if (b > 592) b = 592;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+static int kc_splits(long long P) {
+  for (int S = 296; S > 1; --S)
+    if (P % S == 0 && P / S >= 64) return S;
+  return 1;
+}
+
+}  // namespace hk
+
+using namespace hk;
+
+extern "C" {
+
+int hk_stem_im2col(const float* x_nchw, float* x147, int N, int H, int W, void* stream) {
+  HK_REQUIRE(x_nchw && x147, HK_ERR_ARG, "hk_stem_im2col: null pointer");
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  stem_im2col_kernel<<<rgrid((size_t)N * Ho * Wo * 40, 256), 256, 0, (cudaStream_t)stream>>>(x_nchw, x147, N, H, W, Ho, Wo);
+  HK_LAUNCH_CHECK("stem_im2col_kernel");
+  return 0;
+}
+int hk_pack_stem_weights(const float* w, float* w147, int Cout, void* stream) {
+  HK_REQUIRE(w && w147, HK_ERR_ARG, "hk_pack_stem_weights: null pointer");
+  pack_stem_weights_kernel<<<(Cout * 160 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, w147, Cout);
+  HK_LAUNCH_CHECK("pack_stem_weights_kernel");
+  return 0;
+}
+
+size_t hk_bn_workspace_bytes(long long P, int C) { return (size_t)bn_blocks(P) * 2 * C * sizeof(float); }
+
+int hk_bn_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y, float* save_mean,
+              float* save_invstd, float* running_mean, float* running_var, float momentum, float eps, long long P, int C,
+              int relu, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  HK_REQUIRE(x && gamma && beta && y && save_mean && save_invstd, HK_ERR_ARG, "hk_bn_fwd: null pointer");
+  HK_REQUIRE(C % 4 == 0 && P > 0, HK_ERR_UNSUPPORTED, "hk_bn_fwd: C=%d must be a multiple of 4", C);
+  HK_REQUIRE(workspace && workspace_bytes >= hk_bn_workspace_bytes(P, C), HK_ERR_WORKSPACE, "hk_bn_fwd: workspace too small");
+  float* part = static_cast<float*>(workspace);
+  const int nb = bn_blocks(P);
+  const int C4 = C / 4, clanes = C4 < 256 ? C4 : 256, plan = 256 / clanes;
+  bn_stats_partial_kernel<<<nb, 256, (size_t)2 * plan * C * sizeof(float), st>>>(x, part, P, C);
+  HK_LAUNCH_CHECK("bn_stats_partial_kernel");
+  bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, nb, P, C, eps, momentum, save_mean, save_invstd,
+                                                         running_mean, running_var);
+  HK_LAUNCH_CHECK("bn_stats_finalize_kernel");
+  bn_apply_kernel<<<rgrid((size_t)P * C4, 256), 256, 0, st>>>(x, save_mean, save_invstd, gamma, beta, residual, y,
+                                                            (size_t)P * C4, C4, relu);
+  HK_LAUNCH_CHECK("bn_apply_kernel");
+  return 0;
+}
+
+/* eval-mode / given-statistics apply: y = [relu]((x-mean)*invstd*gamma + beta [+ residual]) */
+int hk_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                const float* residual, float* y, long long P, int C, int relu, void* stream_) {
+  HK_REQUIRE(x && mean && invstd && gamma && beta && y && C % 4 == 0, HK_ERR_ARG, "hk_bn_apply: bad args");
+  bn_apply_kernel<<<rgrid((size_t)P * (C / 4), 256), 256, 0, (cudaStream_t)stream_>>>(x, mean, invstd, gamma, beta, residual, y,
+                                                                                   (size_t)P * (C / 4), C / 4, relu);
+  HK_LAUNCH_CHECK("bn_apply_kernel");
+  return 0;
+}
+
+int hk_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
+              const float* save_invstd, float* dx, float* dres, float* dgamma, float* dbeta, long long P, int C, int relu,
+              void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  HK_REQUIRE(x && dy && gamma && save_mean && save_invstd && dx && dgamma && dbeta && (!relu || y), HK_ERR_ARG,
+             "hk_bn_bwd: null pointer");
+  HK_REQUIRE(C % 4 == 0 && P > 0, HK_ERR_UNSUPPORTED, "hk_bn_bwd: C=%d must be a multiple of 4", C);
+  HK_REQUIRE(workspace && workspace_bytes >= hk_bn_workspace_bytes(P, C), HK_ERR_WORKSPACE, "hk_bn_bwd: workspace too small");
+  float* part = static_cast<float*>(workspace);
+  const int nb = bn_blocks(P);
+  const int C4 = C / 4, clanes = C4 < 256 ? C4 : 256, plan = 256 / clanes;
+  bn_bwd_partial_kernel<<<nb, 256, (size_t)2 * plan * C * sizeof(float), st>>>(x, y, dy, save_mean, save_invstd, part, P, C, relu);
+  HK_LAUNCH_CHECK("bn_bwd_partial_kernel");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, nb, C, dgamma, dbeta);
+  HK_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+  bn_bwd_apply_kernel<<<rgrid((size_t)P * C4, 256), 256, 0, st>>>(x, y, dy, save_mean, save_invstd, gamma, dgamma, dbeta, dx,
+                                                                dres, (size_t)P * C4, C4, 1.f / (float)P, relu);
+  HK_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  return 0;
+}
+
+int hk_maxpool3x3s2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
+  HK_REQUIRE(x && y && C % 4 == 0, HK_ERR_ARG, "hk_maxpool3x3s2_fwd: bad args");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  maxpool3x3s2_fwd_kernel<<<rgrid((size_t)N * Ho * Wo * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, C, Ho, Wo);
+  HK_LAUNCH_CHECK("maxpool3x3s2_fwd_kernel");
+  return 0;
+}
+int hk_maxpool3x3s2_bwd(const float* x, const float* y, const float* dy, float* dx, int N, int H, int W, int C,
+                        void* stream) {
+  HK_REQUIRE(x && y && dy && dx, HK_ERR_ARG, "hk_maxpool3x3s2_bwd: null pointer");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  maxpool3x3s2_bwd_kernel<<<rgrid((size_t)N * H * W * C, 256), 256, 0, (cudaStream_t)stream>>>(x, y, dy, dx, N, H, W, C, Ho, Wo);
+  HK_LAUNCH_CHECK("maxpool3x3s2_bwd_kernel");
+  return 0;
+}
+int hk_subsample2(const float* x, float* y, int N, int H, int W, int C, void* stream) {
+  HK_REQUIRE(x && y && C % 4 == 0, HK_ERR_ARG, "hk_subsample2: bad args");
+  subsample2_kernel<<<rgrid((size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, C / 4);
+  HK_LAUNCH_CHECK("subsample2_kernel");
+  return 0;
+}
+int hk_upsample2_zero(const float* y, float* x, int N, int H, int W, int C, void* stream) {
+  HK_REQUIRE(x && y && C % 4 == 0, HK_ERR_ARG, "hk_upsample2_zero: bad args");
+  upsample2_zero_kernel<<<rgrid((size_t)N * H * W * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(y, x, N, H, W, C / 4);
+  HK_LAUNCH_CHECK("upsample2_zero_kernel");
+  return 0;
+}
+int hk_add_inplace(float* a, const float* b, size_t n, void* stream) {
+  HK_REQUIRE(a && b && n % 4 == 0, HK_ERR_ARG, "hk_add_inplace: bad args");
+  add_inplace_kernel<<<rgrid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n / 4);
+  HK_LAUNCH_CHECK("add_inplace_kernel");
+  return 0;
+}
+int hk_nhwc_to_nchw(const float* x, float* y, int N, int HW, int C, void* stream) {
+  nhwc_to_nchw_kernel<<<rgrid((size_t)N * HW * C, 256), 256, 0, (cudaStream_t)stream>>>(x, y, N, HW, C);
+  HK_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return 0;
+}
+int hk_nchw_to_nhwc(const float* x, float* y, int N, int HW, int C, void* stream) {
+  nchw_to_nhwc_kernel<<<rgrid((size_t)N * HW * C, 256), 256, 0, (cudaStream_t)stream>>>(x, y, N, HW, C);
+  HK_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+  return 0;
+}
+
+/* weight gradient of a matrix-form (1x1 / im2col) convolution: dw [Cout][K] = dY[P][Cout]^T . X[P][K], split-K batched
+ * MN-major tcgen05 GEMM + reduction.  workspace = S * Cout * K floats. */
+size_t hk_matconv_wgrad_workspace_bytes(long long P, int K, int Cout) {
+  return (size_t)kc_splits(P) * Cout * K * sizeof(float);
+}
+int hk_matconv_wgrad(const float* x, const float* dy, float* dw, long long P, int K, int Cout, void* workspace,
+                     size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  HK_REQUIRE(x && dy && dw, HK_ERR_ARG, "hk_matconv_wgrad: null pointer");
+  HK_REQUIRE(K % 4 == 0 && Cout % 4 == 0, HK_ERR_UNSUPPORTED, "hk_matconv_wgrad: K=%d Cout=%d must be multiples of 4", K, Cout);
+  HK_REQUIRE(workspace && workspace_bytes >= hk_matconv_wgrad_workspace_bytes(P, K, Cout), HK_ERR_WORKSPACE,
+             "hk_matconv_wgrad: workspace too small");
+  const int S = kc_splits(P);
+  const long long Kc = P / S;
+  float* part = static_cast<float*>(workspace);
+  GemmEpi e = {};
+  e.C = S == 1 ? dw : part; e.ldc = K; e.strideC = (long long)Cout * K; e.alpha = 1.f;
+  int r = gemm_tf32(dy, 1, Cout, Kc * Cout, x, 1, K, Kc * K, e, Cout, K, (int)Kc, S, st);
+  if (r || S == 1) return r;
+  reduce_partials_kernel<<<rgrid((size_t)Cout * K, 256), 256, 0, st>>>(part, dw, (size_t)Cout * K, S);
+  HK_LAUNCH_CHECK("reduce_partials_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,2 +1,3 @@
 from .bcnn import BCNN, BilinearPooling  # noqa: F401
 from .cbcnn import CBCNN, CompactBilinearPooling  # noqa: F401
+from .mpn import MPN, MPNCOV  # noqa: F401

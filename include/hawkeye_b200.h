@@ -80,6 +80,9 @@ int hk_conv3x3_pack_weights(const float* w, float* w_fwd, float* w_dgrad, int Co
 /* y = relu?(conv3x3(x, w) + bias): implicit GEMM on tcgen05, TMA zero-fill = padding.  Cin%32==0, Cout%32==0. */
 int hk_conv3x3_fwd(const float* x_nhwc, const float* w_fwd_packed, const float* bias, float* y_nhwc, int N, int H,
                    int W, int Cin, int Cout, int relu, void* stream);
+/* same with stride 2 (ResNet v1.5 down-sampling 3x3, resnet.py:116): H, W are the input dims, output is H/2 x W/2 */
+int hk_conv3x3_s2_fwd(const float* x_nhwc, const float* w_fwd_packed, const float* bias, float* y_nhwc, int N, int H,
+                      int W, int Cin, int Cout, int relu, void* stream);
 /* dx = conv3x3^T(dy, w) * (relu_mask_act > 0)  (mask optional: the ReLU output that produced x) */
 int hk_conv3x3_dgrad(const float* dy_nhwc, const float* w_dgrad_packed, const float* relu_mask_act, float* dx_nhwc,
                      int N, int H, int W, int Cin, int Cout, void* stream);
@@ -101,6 +104,37 @@ int hk_maxpool2x2_fwd(const float* x_nhwc, float* y, int N, int H, int W, int C,
 int hk_maxpool2x2_bwd(const float* x_nhwc, const float* dy, float* dx_nhwc, int N, int H, int W, int C, int dy_nchw,
                       void* stream);
 int hk_relu_mask_inplace(float* dy, const float* act, size_t n, void* stream);
+
+/* ---- ResNet-50 v1.5 trunk support (model/backbone/resnet.py:89-252); activations NHWC [P = N*H*W, C] -----------------
+ * stem 7x7/s2/p3 (resnet.py:176): patches X147 [P][160] (+ packed weights [64][160]) feed one tcgen05 GEMM. */
+int hk_stem_im2col(const float* x_nchw, float* x147, int N, int H, int W, void* stream);
+int hk_pack_stem_weights(const float* w, float* w147, int Cout, void* stream);
+/* nn.BatchNorm2d in train mode (batch statistics, running stats updated with momentum, eps inside the sqrt):
+ * y = [relu]((x-mean)*invstd*gamma + beta [+ residual]);  backward returns dx, dgamma, dbeta and (optionally) the
+ * ReLU-masked dy for the residual branch (resnet.py:141-142 `out += identity; relu`). */
+size_t hk_bn_workspace_bytes(long long P, int C);
+int hk_bn_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y, float* save_mean,
+              float* save_invstd, float* running_mean, float* running_var, float momentum, float eps, long long P, int C,
+              int relu, void* workspace, size_t workspace_bytes, void* stream);
+int hk_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                const float* residual, float* y, long long P, int C, int relu, void* stream);
+int hk_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
+              const float* save_invstd, float* dx, float* dres, float* dgamma, float* dbeta, long long P, int C, int relu,
+              void* workspace, size_t workspace_bytes, void* stream);
+/* nn.MaxPool2d(3, 2, 1) (resnet.py:180) */
+int hk_maxpool3x3s2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int hk_maxpool3x3s2_bwd(const float* x, const float* y, const float* dy, float* dx, int N, int H, int W, int C,
+                        void* stream);
+/* stride-2 sampling of an NHWC map (1x1/s2 down-sample convs) and its adjoint (zero insertion); H, W = full-res dims */
+int hk_subsample2(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int hk_upsample2_zero(const float* y, float* x, int N, int H, int W, int C, void* stream);
+int hk_add_inplace(float* a, const float* b, size_t n, void* stream);
+int hk_nhwc_to_nchw(const float* x, float* y, int N, int HW, int C, void* stream);
+int hk_nchw_to_nhwc(const float* x, float* y, int N, int HW, int C, void* stream);
+/* weight gradient of a matrix-form conv (1x1, or im2col'd stem): dw [Cout][K] = dY[P][Cout]^T . X[P][K] */
+size_t hk_matconv_wgrad_workspace_bytes(long long P, int K, int Cout);
+int hk_matconv_wgrad(const float* x, const float* dy, float* dw, long long P, int K, int Cout, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /* ---- classifier nn.Linear (BCNN.py:42, CBCNN.py:26, MPNCOV.py:31) as skinny tcgen05 GEMMs ------------------- */
 size_t hk_linear_fwd_workspace_bytes(int B, int F, int N);

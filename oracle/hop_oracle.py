@@ -295,3 +295,46 @@ def sgd_momentum_step(p, g, buf, lr, momentum, weight_decay, first):
     g = g + weight_decay * p
     buf = g.clone() if first else momentum * buf + g
     return p - lr * buf, buf
+
+
+# --------------------------------------------------------------------------------------
+# ResNet-50 v1.5 trunk (model/backbone/resnet.py:89-252) + MPN (MPNCOV.py:23-102), functional restatement
+# --------------------------------------------------------------------------------------
+RESNET50_LAYERS = ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2))   # (planes, blocks, stride)
+
+
+def _bn_train(x, st, pre, eps=1e-5):
+    """nn.BatchNorm2d in train mode: batch statistics (biased var), affine (resnet.py:114-140 via norm_layer)."""
+    return F.batch_norm(x, None, None, st[pre + '.weight'], st[pre + '.bias'], training=True, eps=eps)
+
+
+def _bottleneck(x, st, pre, stride, has_ds):
+    """Bottleneck.forward (resnet.py:124-144): stride on the 3x3 (v1.5, :116)."""
+    out = F.relu(_bn_train(F.conv2d(x, st[pre + '.conv1.weight']), st, pre + '.bn1'))
+    out = F.relu(_bn_train(F.conv2d(out, st[pre + '.conv2.weight'], stride=stride, padding=1), st, pre + '.bn2'))
+    out = _bn_train(F.conv2d(out, st[pre + '.conv3.weight']), st, pre + '.bn3')
+    identity = x
+    if has_ds:
+        identity = _bn_train(F.conv2d(x, st[pre + '.downsample.0.weight'], stride=stride), st, pre + '.downsample.1')
+    return F.relu(out + identity)
+
+
+def resnet50_trunk_fwd(x, st, prefix='backbone.'):
+    """children()[:-2] of ResNet-50 (MPNCOV.py:28-29): conv1, bn1, relu, maxpool, layer1..4 -> [B,2048,H/32,W/32]."""
+    x = F.conv2d(x, st[prefix + '0.weight'], stride=2, padding=3)
+    x = F.relu(_bn_train(x, st, prefix + '1'))
+    x = F.max_pool2d(x, 3, 2, 1)
+    for li, (planes, blocks, stride) in enumerate(RESNET50_LAYERS):
+        for b in range(blocks):
+            x = _bottleneck(x, st, f'{prefix}{4 + li}.{b}', stride if b == 0 else 1, b == 0)
+    return x
+
+
+def mpn_forward(x, st, iter_num=5):
+    """MPN.forward (MPNCOV.py:33-38) with dimension_reduction (conv_dr_block, :64-69), is_sqrt, is_vec."""
+    f = resnet50_trunk_fwd(x, st)
+    f = F.relu(_bn_train(F.conv2d(f, st['pool.conv_dr_block.0.weight']), st, 'pool.conv_dr_block.1'))
+    c = covpool_fwd(f)
+    s, _ = sqrtm_fwd(c, iter_num)
+    v = triuvec_fwd(s)
+    return F.linear(v.reshape(v.shape[0], -1), st['classifier.weight'], st['classifier.bias'])

@@ -39,3 +39,22 @@ def vgg_bcnn_state(cfg, num_classes, seed=100, feat_dim=None, head_in=None):
     state['classifier.weight'] = det((num_classes, head_in), seed + 5000, (2.0 / head_in) ** 0.5)
     state['classifier.bias'] = det((num_classes,), seed + 5001, 0.01)
     return state
+
+
+def state_like(module, seed=7):
+    """Deterministic state_dict for ANY module (same keys/shapes => same values): per-key seed = crc32(key).
+    conv/linear weights ~ kaiming-scaled normals, BN weight ~ 1 + 0.1 n, biases ~ 0.1 n, running stats untouched."""
+    import zlib
+    out = {}
+    for k, v in module.state_dict().items():
+        ks = seed + (zlib.crc32(k.encode()) & 0x7fffffff)
+        if k.endswith('num_batches_tracked') or k.endswith('running_mean') or k.endswith('running_var'):
+            out[k] = v.clone()
+        elif v.dim() >= 2:
+            fan = v[0].numel()
+            out[k] = det(v.shape, ks, (2.0 / fan) ** 0.5)
+        elif k.endswith('weight'):
+            out[k] = 1.0 + det(v.shape, ks, 0.1)
+        else:
+            out[k] = det(v.shape, ks, 0.1)
+    return out

@@ -108,3 +108,24 @@ def test_cbcnn_model_matches_reference(golden):
     assert rel_l2(logits, golden['cbcnn_logits']) < 1e-4
     assert abs(loss.item() - float(golden['cbcnn_loss'])) < 1e-5
     assert rel_l2(grads['backbone.28.bias'], golden['cbcnn_g_backbone.28.bias']) < 5e-3
+
+
+def test_mpn_model_matches_reference():
+    """ResNet-50 trunk + MPN-COV head restatement vs the UNMODIFIED reference (tests/golden/reference_mpn.npz)."""
+    import os
+    torch.set_num_threads(8)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_mpn.npz'))
+    import hawkeye_b200 as hb
+
+    class Cfg(dict):
+        __getattr__ = dict.__getitem__
+    net = hb.MODEL.get('MPN')(Cfg(name='MPN', iter_num=5, is_sqrt=True, is_vec=True, input_dim=2048,
+                                  dimension_reduction=256, num_classes=200))
+    st = detgen.state_like(net)          # same keys/shapes as the reference model => same deterministic values
+    x = detgen.det((4, 3, 128, 128), 51)
+    labels = detgen.det_labels(4, 200, 52)
+    feat = O.resnet50_trunk_fwd(x, st)
+    assert rel_l2(feat[:, ::16], g['feat_slice']) < 1e-4
+    logits = O.mpn_forward(x, st)
+    assert rel_l2(logits, g['logits']) < 1e-3
+    assert abs(O.cross_entropy_ls(logits, labels).item() - float(g['loss'])) < 1e-4
