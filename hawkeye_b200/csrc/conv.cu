@@ -217,6 +217,218 @@ static int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const Con
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// implicit-GEMM conv v2 (stride 1, maps with W % 16 == 0 and H % 8 == 0): persistent CTAs, halo reuse, double-buffered TMEM.
+//   * pixel tile 16 x 8 of one image (M = 128).  For each (cin chunk, kw) ONE TMA load brings the (8+2) x 16 halo patch
+//     (160 rows x 128 B); the three kh taps are the same patch addressed kh*16 rows (2 KB = whole swizzle atoms) further
+//     down, so the input crosses the L2->SM fabric 3x (+25 % halo) instead of 9x.
+//   * RESIDENT (Cin = 64, BN = 64: VGG conv1_2 and its dgrad): all 9x2 weight tiles (147 KB) stay in shared memory for the
+//     life of the CTA; only activations stream.
+//   * the epilogue of tile i (4 warps, TMEM set i&1) overlaps the TMA/MMA of tile i+1.
+// ------------------------------------------------------------------------------------------------
+template <int BN, bool RESIDENT>
+struct ConvV2Cfg {
+  static constexpr int A_BYTES = 160 * 128;                          // 20 KB halo patch
+  static constexpr int B_TILE = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + (RESIDENT ? 0 : 3 * B_TILE);
+  static constexpr int STAGES = RESIDENT ? 3 : (BN == 64 ? 4 : 3);
+  static constexpr int WRES_BYTES = RESIDENT ? 18 * B_TILE : 0;      // 9 taps x 2 chunks
+  static constexpr int SMEM = STAGES * STAGE_BYTES + WRES_BYTES + 1024 + 512;
+};
+
+template <int BN, bool RESIDENT>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvArgs a,
+                        int n_ntiles, int total_tiles) {
+  using Cfg = ConvV2Cfg<BN, RESIDENT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stages = smem;
+  uint8_t* wres = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(wres + Cfg::WRES_BYTES);
+  uint64_t* empty = full + Cfg::STAGES;
+  uint64_t* acc_full = empty + Cfg::STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* wbar = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunk = a.Cin / 32;
+  const int nkb = nchunk * 3;                       // (chunk, kw) steps per tile
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 2 * BN < 32 ? 32 : 2 * BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (RESIDENT) {   // whole filter bank of this N tile (n_ntiles == 1 by construction): 18 tiles of [BN x 32]
+        mbar_expect_tx(wbar, Cfg::WRES_BYTES);
+        for (int tap = 0; tap < 9; ++tap)
+          for (int ck = 0; ck < 2; ++ck) tma_load_3d(wres + (tap * 2 + ck) * Cfg::B_TILE, &tmW, wbar, ck * 32, 0, tap);
+      }
+      int kbg = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % n_ntiles;
+        int pt = t / n_ntiles;
+        const int tw = pt % a.tiles_w; pt /= a.tiles_w;
+        const int th = pt % a.tiles_h; pt /= a.tiles_h;
+        const int w0 = tw * 16, h0 = th * 8, n0 = pt, co0 = nt * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+          const int s = kbg % Cfg::STAGES;
+          const uint32_t ph = (kbg / Cfg::STAGES) & 1;
+          const int ck = kb / 3, kw = kb - ck * 3;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          uint8_t* st = stages + s * Cfg::STAGE_BYTES;
+          tma_load_4d(st, &tmX, &full[s], ck * 32, w0 + kw - 1, h0 - 1, n0);
+          if (!RESIDENT) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+              tma_load_3d(st + Cfg::A_BYTES + kh * Cfg::B_TILE, &tmW, &full[s], ck * 32, co0, kh * 3 + kw);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
+      if (RESIDENT) { mbar_wait(wbar, 0); tc_fence_after(); }
+      int kbg = 0, itl = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++itl) {
+        const int set = itl & 1;
+        mbar_wait(&acc_empty[set], ((itl >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + set * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+          const int s = kbg % Cfg::STAGES;
+          const uint32_t ph = (kbg / Cfg::STAGES) & 1;
+          const int ck = kb / 3, kw = kb - ck * 3;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(stages + s * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t b_addr = RESIDENT ? smem_u32(wres + ((kh * 3 + kw) * 2 + ck) * Cfg::B_TILE)
+                                             : a_addr + Cfg::A_BYTES + kh * Cfg::B_TILE;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32_ss(d, make_sdesc(a_addr + kh * 2048 + ks * 32, 16, 1024), make_sdesc(b_addr + ks * 32, 16, 1024),
+                           idesc, (kb | kh | ks) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[set]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int wi = r & 15, hi = r >> 4;
+    int itl = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++itl) {
+      const int nt = t % n_ntiles;
+      int pt = t / n_ntiles;
+      const int tw = pt % a.tiles_w; pt /= a.tiles_w;
+      const int th = pt % a.tiles_h; pt /= a.tiles_h;
+      const int w = tw * 16 + wi, h = th * 8 + hi, n = pt, co0 = nt * BN;
+      const size_t pix = ((size_t)n * a.H + h) * a.W + w;
+      const int set = itl & 1;
+      mbar_wait(&acc_full[set], (itl >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + set * BN + c * 32, v);
+        tmem_ld_wait();
+        const int co = co0 + c * 32;
+        if (a.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + co + j);
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (a.mask) {
+          const float4* m = reinterpret_cast<const float4*>(a.mask + pix * a.Cout + co);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 mm = __ldg(m + j);
+            v[4 * j] = mm.x > 0.f ? v[4 * j] : 0.f;
+            v[4 * j + 1] = mm.y > 0.f ? v[4 * j + 1] : 0.f;
+            v[4 * j + 2] = mm.z > 0.f ? v[4 * j + 2] : 0.f;
+            v[4 * j + 3] = mm.w > 0.f ? v[4 * j + 3] : 0.f;
+          }
+        }
+        float4* dst = reinterpret_cast<float4*>(a.Y + pix * a.Cout + co);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(tf32_round(v[4 * j]), tf32_round(v[4 * j + 1]), tf32_round(v[4 * j + 2]),
+                               tf32_round(v[4 * j + 3]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[set]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN < 32 ? 32 : 2 * BN);
+}
+
+template <int BN, bool RESIDENT>
+static int launch_conv_v2(const float* x, const float* wp, ConvArgs a, int N, int H, int W, cudaStream_t stream) {
+  using Cfg = ConvV2Cfg<BN, RESIDENT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_igemm_v2_kernel<BN, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM);
+    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(conv_v2<%d>): %s", BN, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  a.TW = 16; a.TH = 8; a.TN = 1;
+  a.tiles_w = W / 16; a.tiles_h = H / 8; a.tiles_n = N;
+  const int n_ntiles = (a.Cout + BN - 1) / BN;
+  const long long total = (long long)a.tiles_w * a.tiles_h * a.tiles_n * n_ntiles;
+  HK_REQUIRE(total < (1ll << 31), HK_ERR_UNSUPPORTED, "conv3x3: too many tiles");
+  CUtensorMap tmX, tmW;
+  int r;
+  {
+    uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)a.Cin * 4, (uint64_t)W * a.Cin * 4, (uint64_t)H * W * a.Cin * 4};
+    uint32_t box[4] = {32, 16, 10, 1};
+    if ((r = make_tmap(&tmX, x, 4, dims, strides, box))) return r;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)a.Cin, (uint64_t)a.Cout, 9};
+    uint64_t strides[2] = {(uint64_t)a.Cin * 4, (uint64_t)a.Cin * a.Cout * 4};
+    uint32_t box[3] = {32, (uint32_t)BN, 1};
+    if ((r = make_tmap(&tmW, wp, 3, dims, strides, box))) return r;
+  }
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int grid = total < sms ? (int)total : sms;
+  conv3x3_igemm_v2_kernel<BN, RESIDENT><<<grid, 192, Cfg::SMEM, stream>>>(tmX, tmW, a, n_ntiles, (int)total);
+  HK_LAUNCH_CHECK("conv3x3_igemm_v2_kernel");
+  return 0;
+}
+
 // x NHWC [N,H,W,Cin], wp packed [9][Cout][Cin] -> y NHWC [N,H,W,Cout]
 int conv3x3_igemm(const float* x, const float* wp, const float* bias, const float* mask, float* y, int N, int H, int W,
                   int Cin, int Cout, int relu, cudaStream_t stream, int stride = 1) {
@@ -234,6 +446,15 @@ int conv3x3_igemm(const float* x, const float* wp, const float* bias, const floa
   ConvArgs a = {};
   a.Y = y; a.bias = bias; a.mask = mask; a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.relu = relu;
   a.stride = stride;
+  {
+    static int use_v2 = -1;
+    if (use_v2 < 0) { const char* v = getenv("HK_CONV_V2"); use_v2 = v ? atoi(v) : 1; }
+    if (use_v2 && stride == 1 && W % 16 == 0 && H % 8 == 0) {
+      if (Cin == 64 && Cout == 64) return launch_conv_v2<64, true>(x, wp, a, N, H, W, stream);
+      if (Cout <= 64) return launch_conv_v2<64, false>(x, wp, a, N, H, W, stream);
+      return launch_conv_v2<128, false>(x, wp, a, N, H, W, stream);
+    }
+  }
   pick_tile(W, H, N, 128, &a.TW, &a.TH, &a.TN);
   a.tiles_w = (W + a.TW - 1) / a.TW; a.tiles_h = (H + a.TH - 1) / a.TH; a.tiles_n = (N + a.TN - 1) / a.TN;
   HK_REQUIRE((long long)a.tiles_w * a.tiles_h * a.tiles_n < (1ll << 31), HK_ERR_UNSUPPORTED, "conv3x3: grid too large");

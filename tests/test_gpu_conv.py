@@ -19,7 +19,8 @@ def _nchw(t):
     return t.permute(0, 3, 1, 2).contiguous()
 
 
-@pytest.mark.parametrize('N,H,W,Cin,Cout', [(2, 16, 16, 64, 64), (3, 8, 8, 128, 256), (8, 28, 28, 64, 128),
+@pytest.mark.parametrize('N,H,W,Cin,Cout', [(2, 16, 16, 64, 64), (2, 16, 32, 64, 128), (2, 24, 16, 128, 64), (1, 16, 16, 128, 256),
+                                             (3, 8, 8, 128, 256), (8, 28, 28, 64, 128),
                                              (2, 12, 20, 256, 512), (1, 4, 4, 512, 512)])
 def test_conv3x3_fwd_dgrad_wgrad(N, H, W, Cin, Cout):
     from hawkeye_b200 import _lib
