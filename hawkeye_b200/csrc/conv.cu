@@ -117,17 +117,16 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
+      const uint64_t desc_tmpl = make_sdesc(0, 16, 1024);
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % Cfg::STAGES;
         const uint32_t ph = (kb / Cfg::STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
-        const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+        const uint64_t a_base = desc_tmpl + (smem_u32(sA + s * Cfg::A_BYTES) >> 4);
+        const uint64_t b_base = desc_tmpl + (smem_u32(sB + s * Cfg::B_BYTES) >> 4);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_tf32_ss(tmem_base, make_sdesc(a_addr + ks * 32, 16, 1024), make_sdesc(b_addr + ks * 32, 16, 1024), idesc,
-                       (kb | ks) ? 1u : 0u);
+        for (int ks = 0; ks < 4; ++ks) umma_tf32_ss(tmem_base, a_base + ks * 2, b_base + ks * 2, idesc, (kb | ks) ? 1u : 0u);
         umma_commit(&empty[s]);
       }
       umma_commit(accf);
@@ -303,6 +302,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
+      const uint64_t desc_tmpl = make_sdesc(0, 16, 1024);
       if (RESIDENT) { mbar_wait(wbar, 0); tc_fence_after(); }
       int kbg = 0, itl = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++itl) {
@@ -316,15 +316,17 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           const int ck = kb / 3, kw = kb - ck * 3;
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          // descriptors = constant template + (address >> 4); per-MMA work is one 64-bit add per operand
           const uint32_t a_addr = smem_u32(stages + s * Cfg::STAGE_BYTES);
+          const uint64_t a_base = desc_tmpl + (a_addr >> 4);
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
             const uint32_t b_addr = RESIDENT ? smem_u32(wres + ((kh * 3 + kw) * 2 + ck) * Cfg::B_TILE)
                                              : a_addr + Cfg::A_BYTES + kh * Cfg::B_TILE;
+            const uint64_t b_base = desc_tmpl + (b_addr >> 4);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_tf32_ss(d, make_sdesc(a_addr + kh * 2048 + ks * 32, 16, 1024), make_sdesc(b_addr + ks * 32, 16, 1024),
-                           idesc, (kb | kh | ks) ? 1u : 0u);
+              umma_tf32_ss(d, a_base + (kh * 128 + ks * 2), b_base + ks * 2, idesc, (kb | kh | ks) ? 1u : 0u);
           }
           umma_commit(&empty[s]);
         }
@@ -550,10 +552,10 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         for (int kb = 0; kb < nk; ++kb) {
           const int s = kb % WG_STAGES;
           const uint32_t ph = (kb / WG_STAGES) & 1;
-          long long tt = t_begin + kb;
+          int tt = (int)t_begin + kb;
           const int tw = tt % a.tiles_w; tt /= a.tiles_w;
           const int th = tt % a.tiles_h; tt /= a.tiles_h;
-          const int w0 = tw * a.TW, h0 = th * a.TH, n0 = (int)tt * a.TN;
+          const int w0 = tw * a.TW, h0 = th * a.TH, n0 = tt * a.TN;
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], WG_A_BYTES + 3 * patch_rows * a.TN * 128);
           uint8_t* pa = sA + s * WG_A_BYTES;
@@ -569,39 +571,38 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         const uint32_t idesc = make_idesc_tf32(128, 96, 1, 1);
         const uint32_t idesc_b = make_idesc_tf32(128, 16, 1, 1);
         const uint64_t ones_desc = make_sdesc_mn(smem_u32(ones), 0);
+        // The issuing thread is the bottleneck of this kernel (3 N=96 MMAs of 48 cycles per k-step), so everything that
+        // does not depend on the stage is hoisted: per-k-step descriptor offsets (in 16-byte units) are computed once,
+        // and the loop only adds them to the stage's base descriptors.
+        uint32_t a_off[8], b_off[8];
+        {
+          int ks = 0;
+          for (int n = 0; n < a.TN; ++n)
+            for (int j = 0; j < ksteps_img; ++j, ++ks) {
+              a_off[ks] = (uint32_t)((n * img_rows + j * 8) * 128) >> 4;
+              b_off[ks] = (uint32_t)((n * patch_rows + j * 8) * 128) >> 4;
+            }
+        }
+        const uint32_t kh_step = (uint32_t)(a.TW * 128) >> 4;
+        const uint64_t a_tmpl = make_sdesc_mn(0, WG_KP * 128);
+        const uint64_t b_tmpl = make_sdesc_mn(0, WG_B_ONE);
         for (int kb = 0; kb < nk; ++kb) {
           const int s = kb % WG_STAGES;
           const uint32_t ph = (kb / WG_STAGES) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + s * WG_A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + s * WG_B_BYTES);
-          int kstep = 0;
-          for (int n = 0; n < a.TN; ++n) {
-            for (int j = 0; j < ksteps_img; ++j, ++kstep) {
-              const uint32_t accum = (kb | kstep) ? 1u : 0u;
-              const uint64_t ad = make_sdesc_mn(a_addr + (uint32_t)(n * img_rows + j * 8) * 128, WG_KP * 128);
-              // one MMA per kh with N = 96: the three kw patches are three 32-wide N-blocks WG_B_ONE bytes apart (LBO),
-              // so D columns [kh*96 + kw*32, +32) = tap kh*3+kw.  3 MMA issues per k-step instead of 9.
-              if (do_bias && a.dbg == 1) umma_tf32_ss(tmem_base + WG_BIAS_COL, ad, ones_desc, idesc_b, accum);
-              if (a.dbg == 4) {
-                for (int tap = 0; tap < 9; ++tap) {
-                  const int kh = tap / 3, kw = tap - kh * 3;
-                  const uint32_t boff = (uint32_t)(n * patch_rows + kh * a.TW + j * 8) * 128;
-                  umma_tf32_ss(tmem_base + tap * 32, ad, make_sdesc_mn(b_addr + kw * WG_B_ONE + boff, 0),
-                               make_idesc_tf32(128, 32, 1, 1), accum);
-                }
-              } else {
+          const uint64_t a_base = a_tmpl + (smem_u32(sA + s * WG_A_BYTES) >> 4);
+          const uint64_t b_base = b_tmpl + (smem_u32(sB + s * WG_B_BYTES) >> 4);
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
-                  const uint32_t boff = (uint32_t)(n * patch_rows + kh * a.TW + j * 8) * 128;
-                  umma_tf32_ss(tmem_base + kh * 96, ad, make_sdesc_mn(b_addr + boff, WG_B_ONE), idesc, accum);
-                }
-              }
-              if (do_bias && a.dbg != 1)
-                umma_tf32_ss(tmem_base + WG_BIAS_COL, ad, ones_desc, a.dbg == 2 ? make_idesc_tf32(128, 32, 1, 1) : idesc_b,
-                             accum);
-            }
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t accum = (kb | ks) ? 1u : 0u;
+            const uint64_t ad = a_base + a_off[ks];
+            const uint64_t bd = b_base + b_off[ks];
+            if (do_bias && a.dbg == 1) umma_tf32_ss(tmem_base + WG_BIAS_COL, ad, ones_desc, idesc_b, accum);
+            umma_tf32_ss(tmem_base, ad, bd, idesc, accum);
+            umma_tf32_ss(tmem_base + 96, ad, bd + kh_step, idesc, accum);
+            umma_tf32_ss(tmem_base + 192, ad, bd + 2 * kh_step, idesc, accum);
+            if (do_bias && a.dbg != 1) umma_tf32_ss(tmem_base + WG_BIAS_COL, ad, ones_desc, idesc_b, accum);
           }
           umma_commit(&empty[s]);
         }
