@@ -206,6 +206,20 @@ __device__ __forceinline__ float tf32_round(float x) {
   return __uint_as_float(u);
 }
 
+// one lane of a fully converged warp (the MMA warp runs its loop warp-uniformly so descriptor arithmetic stays on the
+// uniform datapath; only the tcgen05 issue itself is predicated on the elected lane)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -300,7 +300,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // warp-uniform loop; tcgen05 issue predicated on one elected lane
       const uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
       const uint64_t desc_tmpl = make_sdesc(0, 16, 1024);
       if (RESIDENT) { mbar_wait(wbar, 0); tc_fence_after(); }
@@ -319,18 +319,25 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           // descriptors = constant template + (address >> 4); per-MMA work is one 64-bit add per operand
           const uint32_t a_addr = smem_u32(stages + s * Cfg::STAGE_BYTES);
           const uint64_t a_base = desc_tmpl + (a_addr >> 4);
+          uint64_t b_base[3];
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
             const uint32_t b_addr = RESIDENT ? smem_u32(wres + ((kh * 3 + kw) * 2 + ck) * Cfg::B_TILE)
                                              : a_addr + Cfg::A_BYTES + kh * Cfg::B_TILE;
-            const uint64_t b_base = desc_tmpl + (b_addr >> 4);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_tf32_ss(d, a_base + (kh * 128 + ks * 2), b_base + ks * 2, idesc, (kb | kh | ks) ? 1u : 0u);
+            b_base[kh] = desc_tmpl + (b_addr >> 4);
           }
-          umma_commit(&empty[s]);
+          if (elect_one()) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_tf32_ss(d, a_base + (kh * 128 + ks * 2), b_base[kh] + ks * 2, idesc, (kb | kh | ks) ? 1u : 0u);
+            umma_commit(&empty[s]);
+          }
+          __syncwarp();
         }
-        umma_commit(&acc_full[set]);
+        if (elect_one()) umma_commit(&acc_full[set]);
+        __syncwarp();
       }
     }
   } else {
@@ -567,13 +574,13 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      {
         const uint32_t idesc = make_idesc_tf32(128, 96, 1, 1);
         const uint32_t idesc_b = make_idesc_tf32(128, 16, 1, 1);
         const uint64_t ones_desc = make_sdesc_mn(smem_u32(ones), 0);
-        // The issuing thread is the bottleneck of this kernel (3 N=96 MMAs of 48 cycles per k-step), so everything that
-        // does not depend on the stage is hoisted: per-k-step descriptor offsets (in 16-byte units) are computed once,
-        // and the loop only adds them to the stage's base descriptors.
+        // The issuing thread is the bottleneck of this kernel (3 N=96 MMAs of 48 cycles per k-step).  The loop runs
+        // warp-uniformly (all 32 lanes) so the descriptor arithmetic is done on the uniform datapath; per-k-step offsets
+        // (16-byte units) are computed once; only the tcgen05 issue is predicated on one elected lane.
         uint32_t a_off[8], b_off[8];
         {
           int ks = 0;
@@ -593,20 +600,23 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
           tc_fence_after();
           const uint64_t a_base = a_tmpl + (smem_u32(sA + s * WG_A_BYTES) >> 4);
           const uint64_t b_base = b_tmpl + (smem_u32(sB + s * WG_B_BYTES) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t accum = (kb | ks) ? 1u : 0u;
-            const uint64_t ad = a_base + a_off[ks];
-            const uint64_t bd = b_base + b_off[ks];
-            if (do_bias && a.dbg == 1) umma_tf32_ss(tmem_base + WG_BIAS_COL, ad, ones_desc, idesc_b, accum);
-            umma_tf32_ss(tmem_base, ad, bd, idesc, accum);
-            umma_tf32_ss(tmem_base + 96, ad, bd + kh_step, idesc, accum);
-            umma_tf32_ss(tmem_base + 192, ad, bd + 2 * kh_step, idesc, accum);
-            if (do_bias && a.dbg != 1) umma_tf32_ss(tmem_base + WG_BIAS_COL, ad, ones_desc, idesc_b, accum);
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint32_t accum = (kb | ks) ? 1u : 0u;
+              const uint64_t ad = a_base + a_off[ks];
+              const uint64_t bd = b_base + b_off[ks];
+              umma_tf32_ss(tmem_base, ad, bd, idesc, accum);
+              umma_tf32_ss(tmem_base + 96, ad, bd + kh_step, idesc, accum);
+              umma_tf32_ss(tmem_base + 192, ad, bd + 2 * kh_step, idesc, accum);
+              if (do_bias) umma_tf32_ss(tmem_base + WG_BIAS_COL, ad, ones_desc, idesc_b, accum);
+            }
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
         }
-        umma_commit(accf);
+        if (elect_one()) umma_commit(accf);
+        __syncwarp();
       }
     } else {
       const int q = warp & 3;
