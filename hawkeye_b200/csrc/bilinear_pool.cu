@@ -164,8 +164,9 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_pair_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // warp-uniform loop; tcgen05 issue predicated on one elected lane
       const uint32_t idesc = make_idesc_tf32(128, 128, 0, 0);
+      const uint64_t desc_tmpl = make_sdesc(0, 16, 1024);
       int kbg = 0, itl = 0;
       for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++itl) {
         const int b = it / ipi;
@@ -181,24 +182,26 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_pair_kernel(const __grid
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t s0 = smem_u32(smem + s * GRAM_STAGE_BYTES);
-          const uint32_t s1 = s0 + GRAM_SLOT;
+          const uint64_t d0 = desc_tmpl + (s0 >> 4), d1 = desc_tmpl + ((s0 + GRAM_SLOT) >> 4);
           const int krem = a.HW - kb * 32;
           const int ksteps = krem >= 32 ? 4 : (krem + 7) / 8;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t d0 = make_sdesc(s0 + ks * 32, 16, 1024);
-            const uint64_t d1 = make_sdesc(s1 + ks * 32, 16, 1024);
-            const uint32_t accum = (kb | ks) ? 1u : 0u;
-            if (diag) {
-              umma_tf32_ss(d_base, d0, d0, idesc, accum);
-              if (blk1 >= 0) umma_tf32_ss(d_base + 128, d1, d1, idesc, accum);
-            } else {
-              umma_tf32_ss(d_base, d0, d1, idesc, accum);        // acc0 = X_blk0 X_blk1^T
-              umma_tf32_ss(d_base + 128, d1, d0, idesc, accum);  // acc1 = X_blk1 X_blk0^T
+          if (elect_one()) {
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint32_t accum = (kb | ks) ? 1u : 0u;
+              if (diag) {
+                umma_tf32_ss(d_base, d0 + ks * 2, d0 + ks * 2, idesc, accum);
+                if (blk1 >= 0) umma_tf32_ss(d_base + 128, d1 + ks * 2, d1 + ks * 2, idesc, accum);
+              } else {
+                umma_tf32_ss(d_base, d0 + ks * 2, d1 + ks * 2, idesc, accum);        // acc0 = X_blk0 X_blk1^T
+                umma_tf32_ss(d_base + 128, d1 + ks * 2, d0 + ks * 2, idesc, accum);  // acc1 = X_blk1 X_blk0^T
+              }
             }
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
         }
-        umma_commit(&acc_full[set]);
+        if (elect_one()) umma_commit(&acc_full[set]);
+        __syncwarp();
       }
     }
   } else {

@@ -115,7 +115,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // warp-uniform loop (descriptor math on the uniform datapath); tcgen05 issue predicated on one elected lane
       const uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
       const uint64_t desc_tmpl = make_sdesc(0, 16, 1024);
       for (int kb = 0; kb < nk; ++kb) {
@@ -125,11 +125,15 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         tc_fence_after();
         const uint64_t a_base = desc_tmpl + (smem_u32(sA + s * Cfg::A_BYTES) >> 4);
         const uint64_t b_base = desc_tmpl + (smem_u32(sB + s * Cfg::B_BYTES) >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) umma_tf32_ss(tmem_base, a_base + ks * 2, b_base + ks * 2, idesc, (kb | ks) ? 1u : 0u);
-        umma_commit(&empty[s]);
+          for (int ks = 0; ks < 4; ++ks) umma_tf32_ss(tmem_base, a_base + ks * 2, b_base + ks * 2, idesc, (kb | ks) ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        __syncwarp();
       }
-      umma_commit(accf);
+      if (elect_one()) umma_commit(accf);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

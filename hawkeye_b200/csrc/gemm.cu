@@ -89,25 +89,30 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // warp-uniform loop; tcgen05 issue predicated on one elected lane
       const uint32_t idesc = make_idesc_tf32(128, BN, a_mn, b_mn);
+      const uint64_t a_tmpl = a_mn ? make_sdesc(0, 4096, mn_sbo, mn_type) : make_sdesc(0, 16, 1024);
+      const uint64_t b_tmpl = b_mn ? make_sdesc(0, 4096, mn_sbo, mn_type) : make_sdesc(0, 16, 1024);
+      const uint32_t a_step = a_mn ? (1024u >> 4) : (32u >> 4);
+      const uint32_t b_step = b_mn ? (1024u >> 4) : (32u >> 4);
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % nstages;
         const uint32_t ph = (kb / nstages) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
-        const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+        const uint64_t a_base = a_tmpl + (smem_u32(sA + s * Cfg::A_BYTES) >> 4);
+        const uint64_t b_base = b_tmpl + (smem_u32(sB + s * Cfg::B_BYTES) >> 4);
         const int krem = K - kb * 32;
         const int ksteps = krem >= 32 ? 4 : (krem + 7) / 8;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t ad = a_mn ? make_sdesc(a_addr + ks * 1024, 4096, mn_sbo, mn_type) : make_sdesc(a_addr + ks * 32, 16, 1024);
-          const uint64_t bd = b_mn ? make_sdesc(b_addr + ks * 1024, 4096, mn_sbo, mn_type) : make_sdesc(b_addr + ks * 32, 16, 1024);
-          umma_tf32_ss(tmem_base, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+        if (elect_one()) {
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_tf32_ss(tmem_base, a_base + ks * a_step, b_base + ks * b_step, idesc, (kb | ks) ? 1u : 0u);
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        __syncwarp();
       }
-      umma_commit(accf);
+      if (elect_one()) umma_commit(accf);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
