@@ -27,10 +27,14 @@ struct GemmCfg {
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Persistent: one CTA per SM walks output tiles t, t+grid, ... (n-tile fastest, so CTAs running at the same time share
+// the A rows through L2).  The smem ring and the two TMEM accumulator sets (2 x BN columns) run across tile
+// boundaries: the epilogue of tile i overlaps the TMA/MMA of tile i+1.
 template <int BN>
-__global__ void __launch_bounds__(192, (BN == 64 ? 3 : (BN == 128 ? 2 : 1)))
+__global__ void __launch_bounds__(192, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpi epi, int M,
-                 int N, int K, int a_mn, int b_mn, int shareA, int shareB, int mn_sbo, int mn_type, int nstages) {
+                 int N, int K, int a_mn, int b_mn, int shareA, int shareB, int mn_sbo, int mn_type, int nstages,
+                 int tiles_m, int tiles_n, int total_tiles) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -38,12 +42,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sB = smem + nstages * Cfg::A_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + nstages * Cfg::STAGE_BYTES);
   uint64_t* empty = full + nstages;
-  uint64_t* accf = empty + nstages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
+  uint64_t* acc_full = empty + nstages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN, bz = blockIdx.z;
   const int nk = (K + 31) / 32;
+  constexpr int TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -52,11 +57,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(accf, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, TCOLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -66,25 +71,32 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      const int bza = shareA ? 0 : bz, bzb = shareB ? 0 : bz;
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % nstages;
-        const uint32_t ph = (kb / nstages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-        uint8_t* a = sA + s * Cfg::A_BYTES;
-        uint8_t* b = sB + s * Cfg::B_BYTES;
-        if (!a_mn) {
-          tma_load_3d(a, &tmA, &full[s], kb * 32, m0, bza);
-        } else {
+      int kbg = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % tiles_n;
+        const int mt = (t / tiles_n) % tiles_m;
+        const int bz = t / (tiles_n * tiles_m);
+        const int m0 = mt * 128, n0 = nt * BN;
+        const int bza = shareA ? 0 : bz, bzb = shareB ? 0 : bz;
+        for (int kb = 0; kb < nk; ++kb, ++kbg) {
+          const int s = kbg % nstages;
+          const uint32_t ph = (kbg / nstages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          uint8_t* a = sA + s * Cfg::A_BYTES;
+          uint8_t* b = sB + s * Cfg::B_BYTES;
+          if (!a_mn) {
+            tma_load_3d(a, &tmA, &full[s], kb * 32, m0, bza);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_3d(a + j * 4096, &tmA, &full[s], m0 + j * 32, kb * 32, bza);
-        }
-        if (!b_mn) {
-          tma_load_3d(b, &tmB, &full[s], kb * 32, n0, bzb);
-        } else {
+            for (int j = 0; j < 4; ++j) tma_load_3d(a + j * 4096, &tmA, &full[s], m0 + j * 32, kb * 32, bza);
+          }
+          if (!b_mn) {
+            tma_load_3d(b, &tmB, &full[s], kb * 32, n0, bzb);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_3d(b + j * 4096, &tmB, &full[s], n0 + j * 32, kb * 32, bzb);
+            for (int j = 0; j < BN / 32; ++j) tma_load_3d(b + j * 4096, &tmB, &full[s], n0 + j * 32, kb * 32, bzb);
+          }
         }
       }
     }
@@ -95,91 +107,109 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint64_t b_tmpl = b_mn ? make_sdesc(0, 4096, mn_sbo, mn_type) : make_sdesc(0, 16, 1024);
       const uint32_t a_step = a_mn ? (1024u >> 4) : (32u >> 4);
       const uint32_t b_step = b_mn ? (1024u >> 4) : (32u >> 4);
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % nstages;
-        const uint32_t ph = (kb / nstages) & 1;
-        mbar_wait(&full[s], ph);
+      int kbg = 0, itl = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++itl) {
+        const int set = itl & 1;
+        mbar_wait(&acc_empty[set], ((itl >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint64_t a_base = a_tmpl + (smem_u32(sA + s * Cfg::A_BYTES) >> 4);
-        const uint64_t b_base = b_tmpl + (smem_u32(sB + s * Cfg::B_BYTES) >> 4);
-        const int krem = K - kb * 32;
-        const int ksteps = krem >= 32 ? 4 : (krem + 7) / 8;
-        if (elect_one()) {
-          for (int ks = 0; ks < ksteps; ++ks)
-            umma_tf32_ss(tmem_base, a_base + ks * a_step, b_base + ks * b_step, idesc, (kb | ks) ? 1u : 0u);
-          umma_commit(&empty[s]);
+        const uint32_t d = tmem_base + set * BN;
+        for (int kb = 0; kb < nk; ++kb, ++kbg) {
+          const int s = kbg % nstages;
+          const uint32_t ph = (kbg / nstages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t a_base = a_tmpl + (smem_u32(sA + s * Cfg::A_BYTES) >> 4);
+          const uint64_t b_base = b_tmpl + (smem_u32(sB + s * Cfg::B_BYTES) >> 4);
+          const int krem = K - kb * 32;
+          const int ksteps = krem >= 32 ? 4 : (krem + 7) / 8;
+          if (elect_one()) {
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_tf32_ss(d, a_base + ks * a_step, b_base + ks * b_step, idesc, (kb | ks) ? 1u : 0u);
+            umma_commit(&empty[s]);
+          }
+          __syncwarp();
         }
+        if (elect_one()) umma_commit(&acc_full[set]);
         __syncwarp();
       }
-      if (elect_one()) umma_commit(accf);
-      __syncwarp();
     }
   } else {
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(accf, 0);
-    tc_fence_after();
-    const float alpha = epi.alpha * (epi.alpha_vec ? epi.alpha_vec[bz] : 1.f);
-    const float beta = epi.beta * (epi.beta_vec ? epi.beta_vec[bz] : 1.f);
-    float* Cb = epi.C + (long long)bz * epi.strideC;
-    const float* Db = epi.D ? epi.D + (long long)bz * epi.strideD : nullptr;
-    const float* Dlb = (epi.D && epi.D_lo) ? epi.D_lo + (long long)bz * epi.strideD : nullptr;
-    const float* Eb = epi.E ? epi.E + (long long)bz * epi.strideC : nullptr;
-    float* Clb = epi.C_lo ? epi.C_lo + (long long)bz * epi.strideC : nullptr;
+    int itl = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++itl) {
+      const int nt = t % tiles_n;
+      const int mt = (t / tiles_n) % tiles_m;
+      const int bz = t / (tiles_n * tiles_m);
+      const int m0 = mt * 128, n0 = nt * BN;
+      const int row = m0 + q * 32 + lane;
+      const int set = itl & 1;
+      mbar_wait(&acc_full[set], (itl >> 1) & 1);
+      tc_fence_after();
+      const float alpha = epi.alpha * (epi.alpha_vec ? epi.alpha_vec[bz] : 1.f);
+      const float beta = epi.beta * (epi.beta_vec ? epi.beta_vec[bz] : 1.f);
+      float* Cb = epi.C + (long long)bz * epi.strideC;
+      const float* Db = epi.D ? epi.D + (long long)bz * epi.strideD : nullptr;
+      const float* Dlb = (epi.D && epi.D_lo) ? epi.D_lo + (long long)bz * epi.strideD : nullptr;
+      const float* Eb = epi.E ? epi.E + (long long)bz * epi.strideC : nullptr;
+      float* Clb = epi.C_lo ? epi.C_lo + (long long)bz * epi.strideC : nullptr;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      const int col0 = n0 + c * 32;
-      if (row < M && col0 < N) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          float acc = v[j];
-          if (Eb && col < N) acc += Eb[(long long)row * epi.ldc + col];
-          float o = alpha * acc;
-          if (col == row) o += epi.diag;
-          if (Db && col < N) {
-            float dv = Db[(long long)row * epi.ldd + col];
-            if (Dlb) dv += Dlb[(long long)row * epi.ldd + col];
-            o += beta * dv;
-          }
-          if (epi.relu & 1) o = fmaxf(o, 0.f);
-          if (epi.relu & 2) o = tf32_round(o);   // output feeds another tf32 MMA: keep its error unbiased
-          v[j] = o;
-        }
-        if (Clb) {   // (hi, lo) split store; not combined with trans_c
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + set * BN + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row < M && col0 < N) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float hi = tf32_round(v[j]);
-            if (col0 + j < N) {
-              Cb[(long long)row * epi.ldc + col0 + j] = hi;
-              Clb[(long long)row * epi.ldc + col0 + j] = tf32_round(v[j] - hi);
+            const int col = col0 + j;
+            float acc = v[j];
+            if (Eb && col < N) acc += Eb[(long long)row * epi.ldc + col];
+            float o = alpha * acc;
+            if (col == row) o += epi.diag;
+            if (Db && col < N) {
+              float dv = Db[(long long)row * epi.ldd + col];
+              if (Dlb) dv += Dlb[(long long)row * epi.ldd + col];
+              o += beta * dv;
             }
+            if (epi.relu & 1) o = fmaxf(o, 0.f);
+            if (epi.relu & 2) o = tf32_round(o);   // output feeds another tf32 MMA: keep its error unbiased
+            v[j] = o;
           }
-        } else if (!epi.trans_c) {
-          float* dst = Cb + (long long)row * epi.ldc + col0;
-          if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          if (Clb) {   // (hi, lo) split store; not combined with trans_c
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; ++j) {
+              const float hi = tf32_round(v[j]);
+              if (col0 + j < N) {
+                Cb[(long long)row * epi.ldc + col0 + j] = hi;
+                Clb[(long long)row * epi.ldc + col0 + j] = tf32_round(v[j] - hi);
+              }
+            }
+          } else if (!epi.trans_c) {
+            float* dst = Cb + (long long)row * epi.ldc + col0;
+            if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < N) dst[j] = v[j];
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) dst[j] = v[j];
+              if (col0 + j < N) Cb[(long long)(col0 + j) * epi.ldc + row] = v[j];
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < N) Cb[(long long)(col0 + j) * epi.ldc + row] = v[j];
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[set]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
 }
 
 static int make_operand_map(CUtensorMap* tm, const float* P, int mn_major, long long ld, long long stride, int rows,
@@ -216,14 +246,23 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(gemm<%d>): %s", BN, cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((M + 127) / 128, (N + BN - 1) / BN, batch);
-  // short-K problems (e.g. the K=32 first-layer GEMM) take only the pipeline stages they can use, so several CTAs
-  // fit per SM and their prologues/epilogues overlap
+  const int tiles_m = (M + 127) / 128, tiles_n = (N + BN - 1) / BN;
+  const long long total = (long long)tiles_m * tiles_n * batch;
+  if (total >= (1ll << 31)) return set_error(HK_ERR_UNSUPPORTED, "gemm: too many tiles");
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
   const int nk = (K + 31) / 32;
-  const int nstages = nk < Cfg::STAGES ? nk : Cfg::STAGES;
+  const long long kblocks_per_cta = (long long)nk * ((total + sms - 1) / sms);
+  const int nstages = kblocks_per_cta < Cfg::STAGES ? (int)kblocks_per_cta : Cfg::STAGES;
   const int smem = nstages * Cfg::STAGE_BYTES + 1024 + 256;
+  const int grid = total < sms ? (int)total : sms;
   umma_gemm_kernel<BN><<<grid, 192, smem, stream>>>(tmA, tmB, epi, M, N, K, a_mn, b_mn, shareA, shareB,
-                                                    dbg_env("HK_DBG_MN_SBO", 512), dbg_env("HK_DBG_MN_TYPE", 1), nstages);
+                                                    dbg_env("HK_DBG_MN_SBO", 512), dbg_env("HK_DBG_MN_TYPE", 1), nstages,
+                                                    tiles_m, tiles_n, (int)total);
   HK_LAUNCH_CHECK("umma_gemm_kernel");
   return 0;
 }

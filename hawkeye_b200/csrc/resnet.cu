@@ -81,10 +81,13 @@ __global__ void bn_stats_partial_kernel(const float* __restrict__ x, float* __re
 __global__ void bn_stats_finalize_kernel(const float* __restrict__ part, int nblk, long long P, int C, float eps,
                                          float momentum, float* __restrict__ mean, float* __restrict__ invstd,
                                          float* __restrict__ rmean, float* __restrict__ rvar) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per channel
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; ++b) { s += part[((size_t)b * 2) * C + c]; q += part[((size_t)b * 2 + 1) * C + c]; }
+  for (int b = lane; b < nblk; b += 32) { s += part[((size_t)b * 2) * C + c]; q += part[((size_t)b * 2 + 1) * C + c]; }
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if (lane != 0) return;
   const double m = s / (double)P;
   double var = q / (double)P - m * m;
   if (var < 0.0) var = 0.0;
@@ -159,10 +162,13 @@ __global__ void bn_bwd_partial_kernel(const float* __restrict__ x, const float* 
 }
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per channel
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; ++b) { s += part[((size_t)b * 2) * C + c]; q += part[((size_t)b * 2 + 1) * C + c]; }
+  for (int b = lane; b < nblk; b += 32) { s += part[((size_t)b * 2) * C + c]; q += part[((size_t)b * 2 + 1) * C + c]; }
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if (lane != 0) return;
   dbeta[c] = (float)s;
   dgamma[c] = (float)q;
 }
@@ -195,8 +201,9 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __
 }
 
 // ------------------------------------------------------------------------------------------------ MaxPool2d(3, 2, 1)
-__global__ void maxpool3x3s2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C,
-                                        int Ho, int Wo) {
+// forward also records, per output element, which of the 9 window positions held the first maximum (PyTorch routing)
+__global__ void maxpool3x3s2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                        unsigned char* __restrict__ arg, int N, int H, int W, int C, int Ho, int Wo) {
   const int C4 = C / 4;
   const size_t total = (size_t)N * Ho * Wo * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -206,55 +213,56 @@ __global__ void maxpool3x3s2_fwd_kernel(const float* __restrict__ x, float* __re
     const int ho = p % Ho;
     const int n = p / Ho;
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    uchar4 am = make_uchar4(0, 0, 0, 0);
     for (int kh = 0; kh < 3; ++kh) {
       const int hh = 2 * ho + kh - 1;
       if (hh < 0 || hh >= H) continue;
       for (int kw = 0; kw < 3; ++kw) {
         const int ww = 2 * wo + kw - 1;
         if (ww < 0 || ww >= W) continue;
-        const float4 v = reinterpret_cast<const float4*>(x + (((size_t)n * H + hh) * W + ww) * C)[c4];
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + hh) * W + ww) * C) + c4);
+        const unsigned char k = (unsigned char)(kh * 3 + kw);
+        if (v.x > m.x) { m.x = v.x; am.x = k; }
+        if (v.y > m.y) { m.y = v.y; am.y = k; }
+        if (v.z > m.z) { m.z = v.z; am.z = k; }
+        if (v.w > m.w) { m.w = v.w; am.w = k; }
       }
     }
     reinterpret_cast<float4*>(y)[i] = m;
+    if (arg) reinterpret_cast<uchar4*>(arg)[i] = am;
   }
 }
-// gather form: dx[pixel] = sum over the (<=4) windows containing it of dy[window] if this pixel is that window's
-// first maximum (PyTorch routing).  No atomics; x is the pool input, y its output.
-__global__ void maxpool3x3s2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                                        const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W,
-                                        int C, int Ho, int Wo) {
-  const size_t total = (size_t)N * H * W * C;
+// gather form (no atomics): an input pixel belongs to <= 2x2 windows; it receives dy of those whose recorded arg-max is it
+__global__ void maxpool3x3s2_bwd_kernel(const unsigned char* __restrict__ arg, const float* __restrict__ dy,
+                                        float* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo) {
+  const int C4 = C / 4;
+  const size_t total = (size_t)N * H * W * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = i % C;
-    size_t p = i / C;
+    const int c4 = i % C4;
+    size_t p = i / C4;
     const int w = p % W; p /= W;
     const int h = p % H;
     const int n = p / H;
-    const float v = x[i];
-    float g = 0.f;
-    for (int ho = (h + 1) / 2 - ((h + 1) % 2 == 0 ? 1 : 0); ho <= (h + 1) / 2; ++ho) {
-      if (ho < 0 || ho >= Ho) continue;
-      for (int wo = (w + 1) / 2 - ((w + 1) % 2 == 0 ? 1 : 0); wo <= (w + 1) / 2; ++wo) {
-        if (wo < 0 || wo >= Wo) continue;
-        const size_t oi = (((size_t)n * Ho + ho) * Wo + wo) * C + c;
-        if (y[oi] != v) continue;
-        // first maximum in scan order inside window (ho, wo)?
-        bool first = true;
-        for (int kh = 0; kh < 3 && first; ++kh) {
-          const int hh = 2 * ho + kh - 1;
-          if (hh < 0 || hh >= H) continue;
-          for (int kw = 0; kw < 3; ++kw) {
-            const int ww = 2 * wo + kw - 1;
-            if (ww < 0 || ww >= W) continue;
-            if (hh == h && ww == w) { kh = 3; break; }
-            if (x[(((size_t)n * H + hh) * W + ww) * C + c] == v) { first = false; break; }
-          }
-        }
-        if (first) g += dy[oi];
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ho0 = h >> 1, wo0 = w >> 1;   // windows ho with 2ho-1 <= h <= 2ho+1: ho0 (+1 if h odd)
+    for (int dh = 0; dh <= (h & 1); ++dh) {
+      const int ho = ho0 + dh;
+      if (ho >= Ho) continue;
+      const int kh = h - 2 * ho + 1;
+      for (int dw = 0; dw <= (w & 1); ++dw) {
+        const int wo = wo0 + dw;
+        if (wo >= Wo) continue;
+        const unsigned char k = (unsigned char)(kh * 3 + (w - 2 * wo + 1));
+        const size_t oi = (((size_t)n * Ho + ho) * Wo + wo) * C4 + c4;
+        const uchar4 am = __ldg(reinterpret_cast<const uchar4*>(arg) + oi);
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dy) + oi);
+        if (am.x == k) g.x += d.x;
+        if (am.y == k) g.y += d.y;
+        if (am.z == k) g.z += d.z;
+        if (am.w == k) g.w += d.w;
       }
     }
-    dx[i] = g;
+    reinterpret_cast<float4*>(dx)[i] = g;
   }
 }
 
@@ -323,7 +331,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restri
 
 static int bn_blocks(long long P) {
   long long b = (P + 255) / 256;
-  if (b > 592) b = 592;
+  if (b > 296) b = 296;
   if (b < 1) b = 1;
   return (int)b;
 }
@@ -367,7 +375,7 @@ int hk_bn_fwd(const float* x, const float* gamma, const float* beta, const float
   const int C4 = C / 4, clanes = C4 < 256 ? C4 : 256, plan = 256 / clanes;
   bn_stats_partial_kernel<<<nb, 256, (size_t)2 * plan * C * sizeof(float), st>>>(x, part, P, C);
   HK_LAUNCH_CHECK("bn_stats_partial_kernel");
-  bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, nb, P, C, eps, momentum, save_mean, save_invstd,
+  bn_stats_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, st>>>(part, nb, P, C, eps, momentum, save_mean, save_invstd,
                                                          running_mean, running_var);
   HK_LAUNCH_CHECK("bn_stats_finalize_kernel");
   bn_apply_kernel<<<rgrid((size_t)P * C4, 256), 256, 0, st>>>(x, save_mean, save_invstd, gamma, beta, residual, y,
@@ -399,7 +407,7 @@ int hk_bn_bwd(const float* x, const float* y, const float* dy, const float* gamm
   const int C4 = C / 4, clanes = C4 < 256 ? C4 : 256, plan = 256 / clanes;
   bn_bwd_partial_kernel<<<nb, 256, (size_t)2 * plan * C * sizeof(float), st>>>(x, y, dy, save_mean, save_invstd, part, P, C, relu);
   HK_LAUNCH_CHECK("bn_bwd_partial_kernel");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, nb, C, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, st>>>(part, nb, C, dgamma, dbeta);
   HK_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   bn_bwd_apply_kernel<<<rgrid((size_t)P * C4, 256), 256, 0, st>>>(x, y, dy, save_mean, save_invstd, gamma, dgamma, dbeta, dx,
                                                                 dres, (size_t)P * C4, C4, 1.f / (float)P, relu);
@@ -407,18 +415,18 @@ int hk_bn_bwd(const float* x, const float* y, const float* dy, const float* gamm
   return 0;
 }
 
-int hk_maxpool3x3s2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
+int hk_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* argmax, int N, int H, int W, int C, void* stream) {
   HK_REQUIRE(x && y && C % 4 == 0, HK_ERR_ARG, "hk_maxpool3x3s2_fwd: bad args");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  maxpool3x3s2_fwd_kernel<<<rgrid((size_t)N * Ho * Wo * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, C, Ho, Wo);
+  maxpool3x3s2_fwd_kernel<<<rgrid((size_t)N * Ho * Wo * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, y, argmax, N, H, W, C, Ho, Wo);
   HK_LAUNCH_CHECK("maxpool3x3s2_fwd_kernel");
   return 0;
 }
-int hk_maxpool3x3s2_bwd(const float* x, const float* y, const float* dy, float* dx, int N, int H, int W, int C,
+int hk_maxpool3x3s2_bwd(const unsigned char* argmax, const float* dy, float* dx, int N, int H, int W, int C,
                         void* stream) {
-  HK_REQUIRE(x && y && dy && dx, HK_ERR_ARG, "hk_maxpool3x3s2_bwd: null pointer");
+  HK_REQUIRE(argmax && dy && dx && C % 4 == 0, HK_ERR_ARG, "hk_maxpool3x3s2_bwd: bad args");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  maxpool3x3s2_bwd_kernel<<<rgrid((size_t)N * H * W * C, 256), 256, 0, (cudaStream_t)stream>>>(x, y, dy, dx, N, H, W, C, Ho, Wo);
+  maxpool3x3s2_bwd_kernel<<<rgrid((size_t)N * H * W * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(argmax, dy, dx, N, H, W, C, Ho, Wo);
   HK_LAUNCH_CHECK("maxpool3x3s2_bwd_kernel");
   return 0;
 }

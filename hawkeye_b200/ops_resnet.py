@@ -188,8 +188,9 @@ class ResNetTrunkFn(Function):
         N, H, W, C = y.shape
         Hp, Wp = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
         p = torch.empty(N, Hp, Wp, C, device=x.device, dtype=torch.float32)
-        _lib.call('hk_maxpool3x3s2_fwd', y, p, N, H, W, C, s)
-        recs.append(('stem', r, (y, p) if save else None))
+        am = torch.empty(N, Hp, Wp, C, device=x.device, dtype=torch.uint8) if save else None
+        _lib.call('hk_maxpool3x3s2_fwd', y, p, am, N, H, W, C, s)
+        recs.append(('stem', r, (tuple(y.shape), am) if save else None))
         cur = p
         for (u1, u2, u3, ds) in plan.blocks:
             w, g, b = pget()
@@ -235,10 +236,10 @@ class ResNetTrunkFn(Function):
                 dx = _add(dx, dres)
             grads = blk + grads
             g = dx
-        _, r0, (y0, p0) = recs[0]
-        N, H, W, C = y0.shape
-        dy0 = torch.empty_like(y0)
-        _lib.call('hk_maxpool3x3s2_bwd', y0, p0, g, dy0, N, H, W, C, s)
+        _, r0, (yshape, am) = recs[0]
+        N, H, W, C = yshape
+        dy0 = torch.empty(N, H, W, C, device=dfeat.device, dtype=torch.float32)
+        _lib.call('hk_maxpool3x3s2_bwd', am, g, dy0, N, H, W, C, s)
         _, _, dw0, dg0, db0 = plan.stem.backward(r0, dy0, need_dx=False)
         grads = [(dw0, dg0, db0)] + grads
         ctx.recs = None

@@ -122,8 +122,9 @@ int hk_bn_bwd(const float* x, const float* y, const float* dy, const float* gamm
               const float* save_invstd, float* dx, float* dres, float* dgamma, float* dbeta, long long P, int C, int relu,
               void* workspace, size_t workspace_bytes, void* stream);
 /* nn.MaxPool2d(3, 2, 1) (resnet.py:180) */
-int hk_maxpool3x3s2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);
-int hk_maxpool3x3s2_bwd(const float* x, const float* y, const float* dy, float* dx, int N, int H, int W, int C,
+/* argmax (optional, [N,Ho,Wo,C] bytes): window position of the first maximum, consumed by the backward */
+int hk_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* argmax, int N, int H, int W, int C, void* stream);
+int hk_maxpool3x3s2_bwd(const unsigned char* argmax, const float* dy, float* dx, int N, int H, int W, int C,
                         void* stream);
 /* stride-2 sampling of an NHWC map (1x1/s2 down-sample convs) and its adjoint (zero insertion); H, W = full-res dims */
 int hk_subsample2(const float* x, float* y, int N, int H, int W, int C, void* stream);

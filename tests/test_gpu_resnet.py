@@ -67,10 +67,11 @@ def test_maxpool3x3_s2_and_stride_helpers():
     ag = _nhwc(a.detach().float()).cuda()
     Ho, Wo = p_ref.shape[2], p_ref.shape[3]
     out = torch.empty(N, Ho, Wo, C, device='cuda')
-    _lib.call('hk_maxpool3x3s2_fwd', ag, out, N, H, W, C, s)
+    am = torch.empty(N, Ho, Wo, C, device='cuda', dtype=torch.uint8)
+    _lib.call('hk_maxpool3x3s2_fwd', ag, out, am, N, H, W, C, s)
     assert torch.equal(_nchw(out).cpu().double(), p_ref.detach())
     dx = torch.empty_like(ag)
-    _lib.call('hk_maxpool3x3s2_bwd', ag, out, _nhwc(g.float()).cuda(), dx, N, H, W, C, s)
+    _lib.call('hk_maxpool3x3s2_bwd', am, _nhwc(g.float()).cuda(), dx, N, H, W, C, s)
     assert rel_l2(_nchw(dx).cpu(), ga) < 1e-6
     sub = torch.empty(N, H // 2, W // 2, C, device='cuda')
     _lib.call('hk_subsample2', ag, sub, N, H, W, C, s)
