@@ -20,6 +20,13 @@ def det_uniform(shape, seed):
     return torch.from_numpy(rs.random_sample(size=tuple(shape)).astype(np.float32))
 
 
+def tf32_rna(t):
+    """Round an fp32 tensor to the nearest TF32-representable value (ties away from zero, like cvt.rna.tf32.f32)."""
+    u = t.contiguous().view(torch.int32)
+    r = ((u + 0x1000) & ~0x1FFF)          # add half an ulp of the 13 dropped bits to the magnitude bits, then truncate
+    return r.view(torch.float32)
+
+
 def det_labels(n, num_classes, seed):
     return torch.from_numpy(np.random.RandomState(seed).randint(0, num_classes, size=n).astype(np.int64))
 

@@ -65,6 +65,13 @@ for d in (8192, 6000):
     (dx,) = torch.autograd.grad(y, x, dy)
     out[f'cbp_y_{d}'] = y.detach().numpy()
     out[f'cbp_dx_{d}'] = dx.numpy()
+    # same op on TF32-representable inputs (what the op sees inside the model: the trunk rounds its activations to tf32):
+    # the tensor-core Gram is then exact, so the ill-conditioned signed-sqrt gradient can be compared tightly
+    x = detgen.tf32_rna(detgen.det_uniform((2, 512, 3, 4), 23)).requires_grad_(True)
+    y = cbp(x)
+    (dx,) = torch.autograd.grad(y, x, detgen.det(y.shape, 24))
+    out[f'cbp_tf32in_y_{d}'] = y.detach().numpy()
+    out[f'cbp_tf32in_dx_{d}'] = dx.numpy()
 
 # ---- MPN-COV (MPNCOV.py:105-230) -------------------------------------------------------------
 for tag, shape, it in (('mpn_small', (2, 16, 3, 3), 5), ('mpn_it3', (2, 24, 4, 4), 3), ('mpn_c256', (1, 256, 14, 14), 5)):
@@ -108,7 +115,7 @@ for stage in (1, 2):
 net = MODEL.get('CBCNN')(rh.cfg(name='CBCNN', stage=2, num_classes=200, input_channel=512, output_channel=8192))
 state = detgen.vgg_bcnn_state(VGG16_D, 200, seed=100, head_in=8192)
 net.load_state_dict(state)
-x = detgen.det((2, 3, 64, 64), 41)
+x = detgen.det((2, 3, 128, 128), 41)   # 4x4 feature map
 labels = detgen.det_labels(2, 200, 42)
 logits = net(x)
 loss = torch.nn.CrossEntropyLoss(label_smoothing=0.1)(logits, labels)

