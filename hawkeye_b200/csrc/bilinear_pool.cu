@@ -407,6 +407,28 @@ static unsigned int* gram_counters() {
   return base + (size_t)(next.fetch_add(1) % GRAM_CNT_REGIONS) * GRAM_CNT_MAXB;
 }
 
+// Tagged tile-sum slots of the single-launch forward: library-owned, zero at module load, never reset (a slot is valid
+// for a launch iff it carries that launch's tag).  Regions are handed out round-robin per call so that calls in flight on
+// different streams do not overwrite each other's slots.
+__device__ unsigned long long g_gram_slots[(size_t)GRAM_CNT_REGIONS * GRAM_CNT_MAXB * 16];
+
+static unsigned long long* gram_slots(unsigned int* tag) {
+  static std::atomic<unsigned> next{0};
+  static thread_local int dev_cached = -1;
+  static thread_local unsigned long long* base = nullptr;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != dev_cached) {
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_gram_slots) != cudaSuccess) return nullptr;
+    base = static_cast<unsigned long long*>(p);
+    dev_cached = dev;
+  }
+  const unsigned n = next.fetch_add(1);
+  *tag = n + 1 ? n + 1 : 1;     // never 0 (the initial slot contents)
+  return base + (size_t)(n % GRAM_CNT_REGIONS) * GRAM_CNT_MAXB * 16;
+}
+
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -442,6 +464,311 @@ static int launch_gram(const CUtensorMap& tm, const GramArgs& a, cudaStream_t st
   }
   HK_LAUNCH_CHECK("gram_pair_kernel");
   return 0;
+}
+
+// =====================================================================================================================
+// K1 (third version): fused Gram + sqrt + L2-normalise with NO pre-kernel and half the tensor-core work.
+//   item   = one 128x128 Gram tile (bi <= bj) of one image, ONE accumulator (128 TMEM columns, 4-slot ring):
+//            off-diagonal tiles are computed once and written twice — block (bj,bi) by the transposed, lane-coalesced
+//            direct stores, block (bi,bj) row-major through 128B-swizzled shared memory + TMA bulk-tensor stores;
+//   norm   = ||z||^2 = sum_ij G_ij / HW + C^2 eps.  Every item publishes the sum of its tile (x2 off the diagonal); the
+//            items of an image meet on a self-resetting arrival counter.  The epilogue is software-pipelined: the sum of
+//            item k+1 is published BEFORE item k is normalised and stored, so the cross-CTA latency hides behind a whole
+//            tile of stores and the MMA warp runs up to three tiles ahead.
+// =====================================================================================================================
+constexpr int GF_STAGES = 4;
+constexpr int GF_SLOTS = 16;              // tagged tile-sum slots per image (>= ipi)
+constexpr int GF_OUT_BYTES = 128 * 128;   // one 128-row x 32-column fp32 box
+constexpr int GF_SMEM = GF_STAGES * GRAM_STAGE_BYTES + 4 * GF_OUT_BYTES + 1024 + 512;
+
+struct GfArgs {
+  int B, C, HW, nblk;
+  float inv_hw, eps;
+  float* Y;
+  float* inv_norm;
+  unsigned long long* slots;   // [B][GF_SLOTS] tagged tile sums {tag:32 | f32 bits:32} (library-owned, never reset)
+  unsigned int tag;            // unique per launch, never 0
+  int store_mode, x_hint;
+  int dbg;               // profiling only (HK_GRAM_DBG): 1 no direct stores, 2 no TMA stores, 4 no norm exchange, 8 no loads/MMA
+};
+
+__device__ __forceinline__ void gf_item(int t, int nblk, int& bi, int& bj) {
+  const int n_off = nblk * (nblk - 1) / 2;
+  if (t < n_off) {
+    int i = 0;
+    while (t >= nblk - 1 - i) { t -= nblk - 1 - i; ++i; }
+    bi = i; bj = i + 1 + t;
+  } else {
+    bi = bj = t - n_off;
+  }
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// positive finite values only (sqrt outputs): round-to-nearest fp32 -> tf32 in two integer ops (cvt.rna.tf32.f32 is
+// emulated with a NaN/Inf check on sm_100a; ties differ only in the direction of exact halves)
+__device__ __forceinline__ float tf32_round_pos(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
+constexpr int GF_THREADS = 352;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 norm exchange
+
+// CT: compile-time C (row pitch of Y in floats) so the 32 transposed stores of a chunk use immediate offsets; 0 = runtime C.
+template <int CT>
+__global__ void __launch_bounds__(GF_THREADS, 1)
+bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, GfArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* outbuf = smem + GF_STAGES * GRAM_STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(outbuf + 4 * GF_OUT_BYTES);
+  uint64_t* empty = full + GF_STAGES;
+  uint64_t* acc_full = empty + GF_STAGES;      // [4]  MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 4;          // [4]  epilogue -> MMA
+  uint64_t* sum_ready = acc_empty + 4;         // [4]  epilogue (8 warps) -> norm warp: tile sums of item k in sum_part[k&3]
+  uint64_t* norm_ready = sum_ready + 4;        // [4]  norm warp -> epilogue: inv_norm of item k in inv_box[k&3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(norm_ready + 4);
+  float* sum_part = reinterpret_cast<float*>(tmem_slot + 2);   // [4][8]
+  float* inv_box = sum_part + 32;                              // [4]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = CT ? CT : a.C;
+  const int ipi = a.nblk * (a.nblk + 1) / 2;     // items (tiles bi <= bj) per image
+  const int total_items = a.B * ipi;
+  const int nk = (a.HW + 31) / 32;
+  const int n_my = (int)blockIdx.x < total_items ? (total_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+    for (int s = 0; s < GF_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8);
+      mbar_init(&sum_ready[s], 8); mbar_init(&norm_ready[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint64_t policy;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+      int kbg = 0;
+      for (int it = blockIdx.x; it < total_items && !(a.dbg & 8); it += gridDim.x) {
+        const int b = it / ipi;
+        int bi, bj;
+        gf_item(it - b * ipi, a.nblk, bi, bj);
+        for (int kb = 0; kb < nk; ++kb, ++kbg) {
+          const int s = kbg % GF_STAGES;
+          const uint32_t ph = (kbg / GF_STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], (bi != bj ? 2 : 1) * GRAM_SLOT);
+          uint8_t* st = smem + s * GRAM_STAGE_BYTES;
+          if (a.x_hint) {
+            tma_load_3d_hint(st, &tmX, &full[s], kb * 32, bi * 128, b, policy);
+            if (bi != bj) tma_load_3d_hint(st + GRAM_SLOT, &tmX, &full[s], kb * 32, bj * 128, b, policy);
+          } else {
+            tma_load_3d(st, &tmX, &full[s], kb * 32, bi * 128, b);
+            if (bi != bj) tma_load_3d(st + GRAM_SLOT, &tmX, &full[s], kb * 32, bj * 128, b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_tf32(128, 128, 0, 0);
+    const uint64_t desc_tmpl = make_sdesc(0, 16, 1024);
+    int kbg = 0, itl = 0;
+    for (int it = blockIdx.x; it < total_items && !(a.dbg & 8); it += gridDim.x, ++itl) {
+      const int b = it / ipi;
+      int bi, bj;
+      gf_item(it - b * ipi, a.nblk, bi, bj);
+      const int slot = itl & 3;
+      mbar_wait(&acc_empty[slot], ((itl >> 2) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + slot * 128;
+      for (int kb = 0; kb < nk; ++kb, ++kbg) {
+        const int s = kbg % GF_STAGES;
+        const uint32_t ph = (kbg / GF_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t s0 = smem_u32(smem + s * GRAM_STAGE_BYTES);
+        const uint64_t d0 = desc_tmpl + (s0 >> 4);
+        const uint64_t d1 = (bi != bj) ? desc_tmpl + ((s0 + GRAM_SLOT) >> 4) : d0;
+        const int krem = a.HW - kb * 32;
+        const int ksteps = krem >= 32 ? 4 : (krem + 7) / 8;
+        if (elect_one()) {
+          for (int ks = 0; ks < ksteps; ++ks) umma_tf32_ss(d, d0 + ks * 2, d1 + ks * 2, idesc, (kb | ks) ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&acc_full[slot]);
+      __syncwarp();
+    }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------ norm exchange (one warp, off the store path).
+    // publish(k): this item's tile sum goes out as ONE 64-bit word {launch tag | f32 bits} into slot t of its image —
+    //             value and validity travel together, so no fence, no counter and no reset are needed;
+    // resolve(k): poll the image's ipi slots (one coalesced load per poll) until every tag is this launch's, reduce the
+    //             values with a fixed shuffle tree (every CTA derives the identical norm), hand 1/||z|| to the epilogue.
+    // publish(k+1) precedes resolve(k): the cross-CTA latency hides behind one whole tile of stores.
+    auto publish = [&](int k) {
+      const int it = blockIdx.x + k * gridDim.x;
+      const int b = it / ipi, t = it - b * ipi;
+      int bi, bj;
+      gf_item(t, a.nblk, bi, bj);
+      const int slot = k & 3;
+      mbar_wait(&sum_ready[slot], (k >> 2) & 1);
+      float v = lane < 8 ? sum_part[slot * 8 + lane] : 0.f;
+      v = warp_sum(v);
+      if (lane == 0) {
+        const float tot = (bi != bj) ? 2.f * v : v;
+        const unsigned long long w = ((unsigned long long)a.tag << 32) | (unsigned long long)__float_as_uint(tot);
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(a.slots + (size_t)b * GF_SLOTS + t), "l"(w) : "memory");
+      }
+      __syncwarp();
+    };
+    if (n_my > 0) publish(0);
+    for (int k = 0; k < n_my; ++k) {
+      if (k + 1 < n_my) publish(k + 1);
+      const int it = blockIdx.x + k * gridDim.x;
+      const int b = it / ipi, t = it - b * ipi;
+      const unsigned long long* ps = a.slots + (size_t)b * GF_SLOTS;
+      unsigned long long w = 0;
+      unsigned int spins = 0;
+      for (;;) {
+        bool ok = true;
+        if (lane < ipi) {
+          asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(ps + lane) : "memory");
+          ok = (unsigned int)(w >> 32) == a.tag;
+        }
+        if (__all_sync(0xffffffffu, ok) || (a.dbg & 4)) break;
+        if (++spins > HK_SPIN_LIMIT) { if (lane == 0) printf("hawkeye_b200: gram norm watchdog (item %d)\n", it); __trap(); }
+      }
+      float g = lane < ipi ? __uint_as_float((unsigned int)w) : 0.f;
+      g = warp_sum(g);
+      if (lane == 0) {
+        const float nrm = sqrtf(g * a.inv_hw + (float)C * (float)C * a.eps);
+        const float inn = 1.f / fmaxf(nrm, 1e-12f);
+        inv_box[k & 3] = inn;
+        mbar_arrive(&norm_ready[k & 3]);
+        if (t == 0 && a.inv_norm) a.inv_norm[b] = inn;
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: 8 warps = 2 groups of 4; group h owns accumulator
+    // columns [64h, 64h+64) (two 32-column chunks), warp q of a group the TMEM lane quarter q.
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const int r = q * 32 + lane;       // accumulator row = row of block bi held by this thread
+    const bool group_leader = (q == 0 && lane == 0);
+    const size_t CC = (size_t)C * C;
+
+    // tile sum of local item k -> sum_part[k&3] (the accumulator stays in TMEM for the store pass)
+    auto tile_sum = [&](int k) {
+      const int slot = k & 3;
+      if (!(a.dbg & 8)) mbar_wait(&acc_full[slot], (k >> 2) & 1);
+      tc_fence_after();
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 2 * h; c < 2 * h + 2; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * 128 + c * 32, v);
+        tmem_ld_wait();
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s4[j & 3] += v[j];
+        sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) {
+        sum_part[slot * 8 + (warp - 2)] = sum;
+        mbar_arrive(&sum_ready[slot]);
+      }
+    };
+
+    if (n_my > 0) tile_sum(0);
+    for (int k = 0; k < n_my; ++k) {
+      if (k + 1 < n_my) tile_sum(k + 1);
+      const int it = blockIdx.x + k * gridDim.x;
+      const int b = it / ipi, t = it - b * ipi;
+      int bi, bj;
+      gf_item(t, a.nblk, bi, bj);
+      const int slot = k & 3;
+      const bool off = (bi != bj) && !(a.dbg & 2);
+      if (off) {     // staging buffers of this group: the TMA stores of the previous off-diagonal item have drained them
+        if (group_leader) bulk_wait_read<0>();
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory");
+      }
+      mbar_wait(&norm_ready[slot], (k >> 2) & 1);
+      const float inv_norm = inv_box[slot];
+#pragma unroll 1
+      for (int c = 2 * h; c < 2 * h + 2; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * 128 + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = tf32_round_pos(fast_sqrt(fmaf(v[j], a.inv_hw, a.eps)) * inv_norm);
+        // block (bj, bi): transposed — lanes run along a row of Y
+        float* y = a.Y + (size_t)b * CC + (size_t)(bj * 128 + c * 32) * C + bi * 128 + r;
+        if (a.dbg & 1) {
+          float keep = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) keep += v[j];
+          if (keep == 123.456f) y[0] = keep;
+        } else if (a.store_mode == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) __stcs(y + (size_t)j * C, v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[(size_t)j * C] = v[j];
+        }
+        if (off) {   // block (bi, bj): row-major via swizzled smem, one TMA store per 128 x 32 box
+          uint8_t* row = outbuf + (2 * h + (c & 1)) * GF_OUT_BYTES + r * 128;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<float4*>(row + ((j4 ^ (r & 7)) << 4)) =
+                make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[slot]);     // 8 warp arrivals free the accumulator slot
+      if (off) {
+        fence_proxy_async();
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory");
+        if (group_leader) {
+          tma_store_3d(&tmY, outbuf + (2 * h) * GF_OUT_BYTES, bj * 128 + 2 * h * 32, bi * 128, b);
+          tma_store_3d(&tmY, outbuf + (2 * h + 1) * GF_OUT_BYTES, bj * 128 + (2 * h + 1) * 32, bi * 128, b);
+          bulk_commit();
+        }
+      }
+    }
+    if (group_leader) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int make_y_map(CUtensorMap* tm, const float* Y, int B, int C) {
+  uint64_t dims[3] = {(uint64_t)C, (uint64_t)C, (uint64_t)B};
+  uint64_t strides[2] = {(uint64_t)C * 4, (uint64_t)C * C * 4};
+  uint32_t box[3] = {32, 128, 1};
+  return make_tmap(tm, Y, 3, dims, strides, box);
 }
 
 static int check_gram_shape(const char* op, const float* X, int B, int C, int HW) {
@@ -510,8 +837,8 @@ using namespace hk;
 extern "C" {
 
 size_t hk_bilinear_pool_fwd_workspace_bytes(int B, int C, int HW) {
-  // unfused variant: channel-sum partials [B][CS][HW]; fused variant: per-item Gram sums [B][ipi]; + inv_norm [B]
-  const int nblk = C / 128, ipi = nblk * (nblk - 1) / 2 + (nblk + 1) / 2;
+  // unfused variant: channel-sum partials [B][CS][HW]; fused variants: per-item Gram sums [B][ipi]; + inv_norm [B]
+  const int nblk = C / 128, ipi = nblk * (nblk + 1) / 2;
   const size_t a = (size_t)B * COLSUM_SPLITS * HW, b = (size_t)B * (ipi > 0 ? ipi : 1);
   return ((a > b ? a : b) + B) * sizeof(float);
 }
@@ -527,13 +854,44 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
   float* partial = static_cast<float*>(workspace);
   float* invn_ws = reinterpret_cast<float*>(static_cast<char*>(workspace) + hk_bilinear_pool_fwd_workspace_bytes(B, C, HW)) - B;
   float* invn = inv_norm_out ? inv_norm_out : invn_ws;
-  const int variant = env_int("HK_GRAM_FUSED", 1);       // 0: K0 channel sums + PDL (first version), 1: fused norm
+  // 0: K0 channel sums + PDL (first version), 1: fused norm on the tile-pair kernel, 2: single-tile items, pipelined norm
+  const int variant = env_int("HK_GRAM_FUSED", 2);
   const int store_mode = env_int("HK_GRAM_STORE", 0);
   const int x_hint = env_int("HK_GRAM_XHINT", 1);
   GramArgs a = {};
   a.C = C; a.HW = HW; a.nblk = C / 128;
   a.inv_hw = 1.f / (float)HW; a.eps = 1e-5f;
   a.store_mode = store_mode; a.x_hint = x_hint;
+  const int ipi3 = a.nblk * (a.nblk + 1) / 2;
+  if (variant >= 2 && ipi3 <= GF_SLOTS) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(bcnn_gram_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(bcnn_gram_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+      if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(bcnn_gram_fwd): %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    GfArgs g = {};
+    g.C = C; g.HW = HW; g.nblk = a.nblk; g.inv_hw = a.inv_hw; g.eps = a.eps; g.store_mode = store_mode; g.x_hint = x_hint;
+    g.dbg = env_int("HK_GRAM_DBG", 0);
+    for (int b0 = 0; b0 < B; b0 += GRAM_CNT_MAXB) {
+      const int nb = B - b0 < GRAM_CNT_MAXB ? B - b0 : GRAM_CNT_MAXB;
+      CUtensorMap tmx, tmy;
+      if ((r = make_x_map(&tmx, x + (size_t)b0 * C * HW, nb, C, HW))) return r;
+      if ((r = make_y_map(&tmy, y + (size_t)b0 * C * C, nb, C))) return r;
+      g.B = nb;
+      g.Y = y + (size_t)b0 * C * C;
+      g.inv_norm = invn + b0;
+      g.slots = gram_slots(&g.tag);
+      HK_REQUIRE(g.slots, HK_ERR_DRIVER, "hk_bilinear_pool_fwd: slot symbol not resolvable");
+      const int grid = gram_grid(nb * ipi3);
+      if (C == 512) bcnn_gram_fwd_kernel<512><<<grid, GF_THREADS, GF_SMEM, stream>>>(tmx, tmy, g);
+      else bcnn_gram_fwd_kernel<0><<<grid, GF_THREADS, GF_SMEM, stream>>>(tmx, tmy, g);
+      HK_LAUNCH_CHECK("bcnn_gram_fwd_kernel");
+    }
+    return 0;
+  }
   const int ipi = a.nblk * (a.nblk - 1) / 2 + (a.nblk + 1) / 2;
   if (!variant || ipi > 148) {
     CUtensorMap tm;

@@ -27,13 +27,14 @@ def check(B=4):
 
 
 def main():
-    variants = [dict(HK_GRAM_FUSED='0'), dict(HK_GRAM_FUSED='1'), dict(HK_GRAM_FUSED='1', HK_GRAM_STORE='1'),
-                dict(HK_GRAM_FUSED='1', HK_GRAM_XHINT='0'), dict(HK_GRAM_FUSED='1', HK_GRAM_STORE='1', HK_GRAM_XHINT='0')]
+    variants = [dict(HK_GRAM_FUSED='0'), dict(HK_GRAM_FUSED='1'), dict(HK_GRAM_FUSED='2'),
+                dict(HK_GRAM_FUSED='2', HK_GRAM_STORE='1'), dict(HK_GRAM_FUSED='2', HK_GRAM_XHINT='0'),
+                dict(HK_GRAM_FUSED='2', HK_GRAM_STORE='1', HK_GRAM_XHINT='0')]
     if len(sys.argv) > 1:
         variants = [dict(kv.split('=') for kv in a.split(',')) for a in sys.argv[1:]]
     out = []
     for v in variants:
-        for k in ('HK_GRAM_FUSED', 'HK_GRAM_STORE', 'HK_GRAM_XHINT', 'HK_GRAM_V'):
+        for k in ('HK_GRAM_FUSED', 'HK_GRAM_STORE', 'HK_GRAM_XHINT', 'HK_GRAM_DBG'):
             os.environ.pop(k, None)
         os.environ.update(v)
         r = dict(variant=v, rel_err=check())
@@ -43,7 +44,7 @@ def main():
                               frac=round(B * bench.K1_FWD_BYTES_PER_IMG / t / 1e9 / peak, 4))
         print(json.dumps(r), flush=True)
         out.append(r)
-    for k in ('HK_GRAM_FUSED', 'HK_GRAM_STORE', 'HK_GRAM_XHINT', 'HK_GRAM_V'):
+    for k in ('HK_GRAM_FUSED', 'HK_GRAM_STORE', 'HK_GRAM_XHINT', 'HK_GRAM_DBG'):
         os.environ.pop(k, None)
     # backward (two kernels + GEMM), same protocol
     for B in (32, 256):
