@@ -38,6 +38,9 @@ int hk_gemm_tf32(const float* A, int a_mn_major, long long lda, long long stride
  * x [B,C,HW] (NCHW feature map viewed as in BCNN.py:17) -> y [B,C*C] = normalize(sqrt(x x^T/HW + 1e-5)).
  * inv_norm_out (optional, [B]) receives 1/||z||.  Requires C%128==0, HW%4==0. */
 size_t hk_bilinear_pool_fwd_workspace_bytes(int B, int C, int HW);
+/* profiling aid (no reference counterpart): per-CTA %globaltimer stamps of the following hk_bilinear_pool_fwd launches are
+ * written to buf ([148][16] unsigned long long, device memory); NULL switches it off. */
+void hk_debug_gram_trace(void* buf);
 int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, int C, int HW, void* workspace,
                          size_t workspace_bytes, void* stream);
 /* backward of the same (what autograd derives for BCNN.py:13-27): dx [B,C,HW] from dy [B,C*C]; z is recomputed. */
