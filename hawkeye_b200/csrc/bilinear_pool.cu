@@ -495,7 +495,6 @@ struct GfArgs {
   unsigned long long* trace;   // profiling only: [grid][16] globaltimer stamps (hk_debug_gram_trace), or null
   int stages;                  // 2..GF_STAGES
   int pdl;                     // launched with programmatic stream serialization
-  int pair_diag;               // diagonal tiles ride with an off-diagonal group (fewer operand loads, coarser TMEM ring)
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -534,41 +533,6 @@ __device__ __forceinline__ float tf32_round_pos(float x) {
 constexpr int GF_THREADS = 352;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 norm exchange
 
 // CT: compile-time C (row pitch of Y in floats) so the 32 transposed stores of a chunk use immediate offsets; 0 = runtime C.
-// Work decomposition.  A *group* = one off-diagonal tile (bi < bj) of one image, optionally carrying the diagonal tile of
-// one of its two row blocks (diag d rides with tile (d, d+1); the last one with tile (0, nblk-1)), so a diagonal tile
-// costs no operand traffic of its own: nblk(nblk-1)/2 groups per image load 2 row blocks each and produce nblk^2 output
-// blocks (1.17 bytes loaded per byte stored at nblk = 4 instead of 1.56).  Groups go round-robin to the persistent CTAs;
-// inside a CTA the epilogue and the norm warp see a plain sequence of single-accumulator *tiles*.
-struct GfTile {
-  int gi;      // global group index
-  int sub;     // 0: the off-diagonal tile, 1: the diagonal tile riding with it
-  int c;       // running tile count of this CTA (TMEM slot = c & 3, mbarrier use = c >> 2)
-  int b, t;    // image, tile id within the image (slot of its tile sum): off-diagonal 0..n_off-1, diagonal n_off + d
-  int bi, bj;  // row-block pair of the tile (bi == bj on the diagonal)
-  int dg;      // diagonal block riding with this group, or -1
-};
-
-// gpi == n_off: diagonal tiles ride with off-diagonal groups; gpi == n_off + nblk: every diagonal tile is its own group.
-__device__ __forceinline__ void gf_decode(GfTile& x, int nblk, int gpi) {
-  const int n_off = nblk * (nblk - 1) / 2;
-  x.b = x.gi / gpi;
-  const int g = x.gi - x.b * gpi;
-  if (g >= n_off) { x.bi = x.bj = g - n_off; x.dg = -1; x.t = g; return; }
-  int i = 0, r = g;
-  while (r >= nblk - 1 - i) { r -= nblk - 1 - i; ++i; }
-  const int bi = i, bj = i + 1 + r;
-  x.dg = (gpi != n_off) ? -1 : ((bj == bi + 1) ? bi : ((bi == 0 && bj == nblk - 1) ? nblk - 1 : -1));
-  if (x.sub == 0) { x.bi = bi; x.bj = bj; x.t = g; }
-  else { x.bi = x.bj = x.dg; x.t = n_off + x.dg; }
-}
-__device__ __forceinline__ void gf_next(GfTile& x, int nblk, int gpi, int total_groups) {
-  if (x.sub == 0 && x.dg >= 0) x.sub = 1;
-  else { x.gi += gridDim.x; x.sub = 0; }
-  ++x.c;
-  if (x.gi < total_groups) gf_decode(x, nblk, gpi);
-}
-
-// CT: compile-time C (row pitch of Y in floats) so the 32 transposed stores of a chunk use immediate offsets; 0 = runtime C.
 template <int CT>
 __global__ void __launch_bounds__(GF_THREADS, 1)
 bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, GfArgs a) {
@@ -579,18 +543,18 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint64_t* empty = full + GF_STAGES;
   uint64_t* acc_full = empty + GF_STAGES;      // [4]  MMA -> epilogue
   uint64_t* acc_empty = acc_full + 4;          // [4]  epilogue -> MMA
-  uint64_t* sum_ready = acc_empty + 4;         // [4]  epilogue (8 warps) -> norm warp: tile sums of tile c in sum_part[c&3]
-  uint64_t* norm_ready = sum_ready + 4;        // [4]  norm warp -> epilogue: inv_norm of tile c in inv_box[c&3]
+  uint64_t* sum_ready = acc_empty + 4;         // [4]  epilogue (8 warps) -> norm warp: tile sums of item k in sum_part[k&3]
+  uint64_t* norm_ready = sum_ready + 4;        // [4]  norm warp -> epilogue: inv_norm of item k in inv_box[k&3]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(norm_ready + 4);
   float* sum_part = reinterpret_cast<float*>(tmem_slot + 2);   // [4][8]
   float* inv_box = sum_part + 32;                              // [4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = CT ? CT : a.C;
-  const int ipi = a.nblk * (a.nblk + 1) / 2;                       // tiles per image
-  const int gpi = a.pair_diag ? ipi - a.nblk : ipi;                // groups per image
-  const int total_groups = a.B * gpi;
+  const int ipi = a.nblk * (a.nblk + 1) / 2;     // items (tiles bi <= bj) per image
+  const int total_items = a.B * ipi;
   const int nk = (a.HW + 31) / 32;
+  const int n_my = (int)blockIdx.x < total_items ? (total_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -621,22 +585,22 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       uint64_t policy;
       asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
       int kbg = 0;
-      for (int gi = blockIdx.x; gi < total_groups && !(a.dbg & 8); gi += gridDim.x) {
-        GfTile x; x.gi = gi; x.sub = 0; x.c = 0;
-        gf_decode(x, a.nblk, gpi);
+      for (int it = blockIdx.x; it < total_items && !(a.dbg & 8); it += gridDim.x) {
+        const int b = it / ipi;
+        int bi, bj;
+        gf_item(it - b * ipi, a.nblk, bi, bj);
         for (int kb = 0; kb < nk; ++kb, ++kbg) {
           const int s = kbg % a.stages;
           const uint32_t ph = (kbg / a.stages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          const bool two_ops = x.bi != x.bj;
-          mbar_expect_tx(&full[s], (two_ops ? 2 : 1) * GRAM_SLOT);
+          mbar_expect_tx(&full[s], (bi != bj ? 2 : 1) * GRAM_SLOT);
           uint8_t* st = smem + s * GRAM_STAGE_BYTES;
           if (a.x_hint) {
-            tma_load_3d_hint(st, &tmX, &full[s], kb * 32, x.bi * 128, x.b, policy);
-            if (two_ops) tma_load_3d_hint(st + GRAM_SLOT, &tmX, &full[s], kb * 32, x.bj * 128, x.b, policy);
+            tma_load_3d_hint(st, &tmX, &full[s], kb * 32, bi * 128, b, policy);
+            if (bi != bj) tma_load_3d_hint(st + GRAM_SLOT, &tmX, &full[s], kb * 32, bj * 128, b, policy);
           } else {
-            tma_load_3d(st, &tmX, &full[s], kb * 32, x.bi * 128, x.b);
-            if (two_ops) tma_load_3d(st + GRAM_SLOT, &tmX, &full[s], kb * 32, x.bj * 128, x.b);
+            tma_load_3d(st, &tmX, &full[s], kb * 32, bi * 128, b);
+            if (bi != bj) tma_load_3d(st + GRAM_SLOT, &tmX, &full[s], kb * 32, bj * 128, b);
           }
         }
       }
@@ -644,17 +608,15 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_tf32(128, 128, 0, 0);
     const uint64_t desc_tmpl = make_sdesc(0, 16, 1024);
-    int kbg = 0, c = 0;     // c: running tile count (TMEM slot ring)
-    for (int gi = blockIdx.x; gi < total_groups && !(a.dbg & 8); gi += gridDim.x) {
-      GfTile x; x.gi = gi; x.sub = 0; x.c = 0;
-      gf_decode(x, a.nblk, gpi);
-      const bool two = x.dg >= 0;
-      const int s_off = c & 3, s_dg = (c + 1) & 3;
-      mbar_wait(&acc_empty[s_off], ((c >> 2) & 1) ^ 1);
-      if (two) mbar_wait(&acc_empty[s_dg], (((c + 1) >> 2) & 1) ^ 1);
+    int kbg = 0, itl = 0;
+    for (int it = blockIdx.x; it < total_items && !(a.dbg & 8); it += gridDim.x, ++itl) {
+      const int b = it / ipi;
+      int bi, bj;
+      gf_item(it - b * ipi, a.nblk, bi, bj);
+      const int slot = itl & 3;
+      mbar_wait(&acc_empty[slot], ((itl >> 2) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d_off = tmem_base + s_off * 128, d_dg = tmem_base + s_dg * 128;
-      const uint32_t dg_slot_bytes = (two && x.dg == x.bj) ? GRAM_SLOT : 0;
+      const uint32_t d = tmem_base + slot * 128;
       for (int kb = 0; kb < nk; ++kb, ++kbg) {
         const int s = kbg % a.stages;
         const uint32_t ph = (kbg / a.stages) & 1;
@@ -663,82 +625,68 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (tr && kbg == 0 && lane == 0) tr[1] = gtimer();
         const uint32_t s0 = smem_u32(smem + s * GRAM_STAGE_BYTES);
         const uint64_t d0 = desc_tmpl + (s0 >> 4);
-        const uint64_t d1 = (x.bi != x.bj) ? desc_tmpl + ((s0 + GRAM_SLOT) >> 4) : d0;
-        const uint64_t dd = desc_tmpl + ((s0 + dg_slot_bytes) >> 4);
+        const uint64_t d1 = (bi != bj) ? desc_tmpl + ((s0 + GRAM_SLOT) >> 4) : d0;
         const int krem = a.HW - kb * 32;
         const int ksteps = krem >= 32 ? 4 : (krem + 7) / 8;
         if (elect_one()) {
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t accum = (kb | ks) ? 1u : 0u;
-            umma_tf32_ss(d_off, d0 + ks * 2, d1 + ks * 2, idesc, accum);          // X_bi X_bj^T
-            if (two) umma_tf32_ss(d_dg, dd + ks * 2, dd + ks * 2, idesc, accum);  // X_d X_d^T from the same stage
-          }
+          for (int ks = 0; ks < ksteps; ++ks) umma_tf32_ss(d, d0 + ks * 2, d1 + ks * 2, idesc, (kb | ks) ? 1u : 0u);
           umma_commit(&empty[s]);
         }
         __syncwarp();
       }
-      if (elect_one()) {
-        umma_commit(&acc_full[s_off]);
-        if (two) umma_commit(&acc_full[s_dg]);
-      }
+      if (elect_one()) umma_commit(&acc_full[slot]);
       __syncwarp();
-      c += two ? 2 : 1;
     }
   } else if (warp == 10) {
     // ------------------------------------------------------------ norm exchange (one warp, off the store path).
-    // publish(tile): its sum goes out as ONE 64-bit word {launch tag | f32 bits} into slot t of its image — value and
-    //                validity travel together, so no fence, no counter and no reset are needed;
-    // resolve(tile): poll the image's ipi slots (one coalesced load per poll) until every tag is this launch's, reduce the
-    //                values with a fixed shuffle tree (every CTA derives the identical norm), hand 1/||z|| to the epilogue.
-    // Publishing runs ahead of resolving whenever a tile sum is available, so in steady state the cross-CTA latency hides
-    // behind a whole tile of stores; neither ever blocks the other.
-    GfTile pub, res;
-    pub.gi = res.gi = blockIdx.x; pub.sub = res.sub = 0; pub.c = res.c = 0;
-    if (pub.gi < total_groups) { gf_decode(pub, a.nblk, gpi); res = pub; }
-    unsigned int spins = 0;
-    while (res.gi < total_groups) {
-      bool progress = false;
-      if (pub.gi < total_groups && pub.c < res.c + 4 && mbar_test_wait(&sum_ready[pub.c & 3], (pub.c >> 2) & 1)) {
-        float v = lane < 8 ? sum_part[(pub.c & 3) * 8 + lane] : 0.f;
-        v = warp_sum(v);
-        if (lane == 0) {
-          const float tot = (pub.bi != pub.bj) ? 2.f * v : v;
-          const unsigned long long w = ((unsigned long long)a.tag << 32) | (unsigned long long)__float_as_uint(tot);
-          asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(a.slots + (size_t)pub.b * GF_SLOTS + pub.t), "l"(w)
-                       : "memory");
-        }
-        __syncwarp();
-        gf_next(pub, a.nblk, gpi, total_groups);
-        progress = true;
+    // publish(k): this item's tile sum goes out as ONE 64-bit word {launch tag | f32 bits} into slot t of its image —
+    //             value and validity travel together, so no fence, no counter and no reset are needed;
+    // resolve(k): poll the image's ipi slots (one coalesced load per poll) until every tag is this launch's, reduce the
+    //             values with a fixed shuffle tree (every CTA derives the identical norm), hand 1/||z|| to the epilogue.
+    // publish(k+1) precedes resolve(k): the cross-CTA latency hides behind one whole tile of stores.
+    auto publish = [&](int k) {
+      const int it = blockIdx.x + k * gridDim.x;
+      const int b = it / ipi, t = it - b * ipi;
+      int bi, bj;
+      gf_item(t, a.nblk, bi, bj);
+      const int slot = k & 3;
+      mbar_wait(&sum_ready[slot], (k >> 2) & 1);
+      float v = lane < 8 ? sum_part[slot * 8 + lane] : 0.f;
+      v = warp_sum(v);
+      if (lane == 0) {
+        const float tot = (bi != bj) ? 2.f * v : v;
+        const unsigned long long w = ((unsigned long long)a.tag << 32) | (unsigned long long)__float_as_uint(tot);
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(a.slots + (size_t)b * GF_SLOTS + t), "l"(w) : "memory");
       }
-      if (res.c < pub.c || (a.dbg & 4)) {
-        const unsigned long long* ps = a.slots + (size_t)res.b * GF_SLOTS;
-        unsigned long long w = 0;
+      __syncwarp();
+    };
+    if (n_my > 0) publish(0);
+    for (int k = 0; k < n_my; ++k) {
+      if (k + 1 < n_my) publish(k + 1);
+      const int it = blockIdx.x + k * gridDim.x;
+      const int b = it / ipi, t = it - b * ipi;
+      const unsigned long long* ps = a.slots + (size_t)b * GF_SLOTS;
+      unsigned long long w = 0;
+      unsigned int spins = 0;
+      for (;;) {
         bool ok = true;
         if (lane < ipi) {
           asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(ps + lane) : "memory");
           ok = (unsigned int)(w >> 32) == a.tag;
         }
-        if (__all_sync(0xffffffffu, ok) || ((a.dbg & 4) && res.c < pub.c)) {
-          float g = lane < ipi ? __uint_as_float((unsigned int)w) : 0.f;
-          g = warp_sum(g);
-          if (lane == 0) {
-            const float nrm = sqrtf(g * a.inv_hw + (float)C * (float)C * a.eps);
-            const float inn = 1.f / fmaxf(nrm, 1e-12f);
-            inv_box[res.c & 3] = inn;
-            mbar_arrive(&norm_ready[res.c & 3]);
-            if (res.t == 0 && a.inv_norm) a.inv_norm[res.b] = inn;
-          }
-          __syncwarp();
-          gf_next(res, a.nblk, gpi, total_groups);
-          progress = true;
-        }
+        if (__all_sync(0xffffffffu, ok) || (a.dbg & 4)) break;
+        if (++spins > HK_SPIN_LIMIT) { if (lane == 0) printf("hawkeye_b200: gram norm watchdog (item %d)\n", it); __trap(); }
       }
-      if (progress) spins = 0;
-      else if (++spins > HK_SPIN_LIMIT) {
-        if (lane == 0) printf("hawkeye_b200: gram norm watchdog (block %d group %d)\n", blockIdx.x, res.gi);
-        __trap();
+      float g = lane < ipi ? __uint_as_float((unsigned int)w) : 0.f;
+      g = warp_sum(g);
+      if (lane == 0) {
+        const float nrm = sqrtf(g * a.inv_hw + (float)C * (float)C * a.eps);
+        const float inn = 1.f / fmaxf(nrm, 1e-12f);
+        inv_box[k & 3] = inn;
+        mbar_arrive(&norm_ready[k & 3]);
+        if (t == 0 && a.inv_norm) a.inv_norm[b] = inn;
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue: 8 warps = 2 groups of 4; group h owns accumulator
@@ -749,12 +697,12 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const bool group_leader = (q == 0 && lane == 0);
     const size_t CC = (size_t)C * C;
 
-    // tile sum -> sum_part[c&3] (the accumulator stays in TMEM for the store pass)
-    auto tile_sum = [&](const GfTile& x) {
-      const int slot = x.c & 3;
-      if (!(a.dbg & 8)) mbar_wait(&acc_full[slot], (x.c >> 2) & 1);
+    // tile sum of local item k -> sum_part[k&3] (the accumulator stays in TMEM for the store pass)
+    auto tile_sum = [&](int k) {
+      const int slot = k & 3;
+      if (!(a.dbg & 8)) mbar_wait(&acc_full[slot], (k >> 2) & 1);
       tc_fence_after();
-      if (tr && x.c < 4 && threadIdx.x == 64) tr[2 + x.c] = gtimer();
+      if (tr && k < 4 && threadIdx.x == 64) tr[2 + k] = gtimer();
       float sum = 0.f;
 #pragma unroll 1
       for (int c = 2 * h; c < 2 * h + 2; ++c) {
@@ -773,28 +721,22 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
     };
 
-    GfTile cur;
-    cur.gi = blockIdx.x; cur.sub = 0; cur.c = 0;
-    if (cur.gi < total_groups) { gf_decode(cur, a.nblk, gpi); tile_sum(cur); }
-    while (cur.gi < total_groups) {
-      GfTile nxt = cur;
-      gf_next(nxt, a.nblk, gpi, total_groups);
-      const bool has_next = nxt.gi < total_groups;
-      // sum the next tile first if its accumulator is already complete (steady state: the MMA warp runs ahead); otherwise
-      // store this one first — never stall finished work behind unfinished work
-      bool early = has_next && ((a.dbg & 8) || mbar_test_wait(&acc_full[nxt.c & 3], (nxt.c >> 2) & 1));
-      early = __shfl_sync(0xffffffffu, early ? 1 : 0, 0) != 0;    // warp-uniform (tcgen05.ld is warp-collective)
-      if (early) tile_sum(nxt);
-      const int slot = cur.c & 3;
-      const int b = cur.b, bi = cur.bi, bj = cur.bj;
+    if (n_my > 0) tile_sum(0);
+    for (int k = 0; k < n_my; ++k) {
+      if (k + 1 < n_my) tile_sum(k + 1);
+      const int it = blockIdx.x + k * gridDim.x;
+      const int b = it / ipi, t = it - b * ipi;
+      int bi, bj;
+      gf_item(t, a.nblk, bi, bj);
+      const int slot = k & 3;
       const bool off = (bi != bj) && !(a.dbg & 2);
-      if (off) {     // staging buffers of this group: the TMA stores of the previous off-diagonal tile have drained them
+      if (off) {     // staging buffers of this group: the TMA stores of the previous off-diagonal item have drained them
         if (group_leader) bulk_wait_read<0>();
         asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory");
       }
-      mbar_wait(&norm_ready[slot], (cur.c >> 2) & 1);
+      mbar_wait(&norm_ready[slot], (k >> 2) & 1);
       const float inv_norm = inv_box[slot];
-      if (tr && cur.c < 4 && threadIdx.x == 64) tr[6 + cur.c] = gtimer();
+      if (tr && k < 4 && threadIdx.x == 64) tr[6 + k] = gtimer();
 #pragma unroll 1
       for (int c = 2 * h; c < 2 * h + 2; ++c) {
         float v[32];
@@ -836,9 +778,7 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           bulk_commit();
         }
       }
-      if (tr && cur.c < 4 && threadIdx.x == 64) tr[10 + cur.c] = gtimer();
-      if (has_next && !early) tile_sum(nxt);
-      cur = nxt;
+      if (tr && k < 4 && threadIdx.x == 64) tr[10 + k] = gtimer();
     }
     if (group_leader) bulk_wait_all();
     if (tr && threadIdx.x == 64) tr[14] = gtimer();
@@ -950,7 +890,7 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
   a.inv_hw = 1.f / (float)HW; a.eps = 1e-5f;
   a.store_mode = store_mode; a.x_hint = x_hint;
   const int ipi3 = a.nblk * (a.nblk + 1) / 2;
-  if (variant >= 2 && ipi3 <= GF_SLOTS && a.nblk >= 3) {
+  if (variant >= 2 && ipi3 <= GF_SLOTS) {
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(bcnn_gram_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
@@ -967,7 +907,6 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
     if (g.stages < 2) g.stages = 2;
     if (g.stages > GF_STAGES) g.stages = GF_STAGES;
     g.pdl = env_int("HK_GRAM_PDL", 1);
-    g.pair_diag = env_int("HK_GRAM_PAIR", 0);
     for (int b0 = 0; b0 < B; b0 += GRAM_CNT_MAXB) {
       const int nb = B - b0 < GRAM_CNT_MAXB ? B - b0 : GRAM_CNT_MAXB;
       CUtensorMap tmx, tmy;
@@ -978,7 +917,7 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
       g.inv_norm = invn + b0;
       g.slots = gram_slots(&g.tag);
       HK_REQUIRE(g.slots, HK_ERR_DRIVER, "hk_bilinear_pool_fwd: slot symbol not resolvable");
-      const int grid = gram_grid(nb * (g.pair_diag ? a.nblk * (a.nblk - 1) / 2 : ipi3));
+      const int grid = gram_grid(nb * ipi3);
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(grid);
       cfg.blockDim = dim3(GF_THREADS);

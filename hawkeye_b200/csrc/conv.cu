@@ -678,9 +678,29 @@ int conv3x3_wgrad(const float* x, const float* dy, float* dwp, float* db, int N,
   a.tiles_w = (W + a.TW - 1) / a.TW; a.tiles_h = (H + a.TH - 1) / a.TH; a.tiles_n = (N + a.TN - 1) / a.TN;
   const long long out_tiles = (long long)((Cout + 127) / 128) * (Cin / 32);
   const long long total_tiles = (long long)a.tiles_w * a.tiles_h * a.tiles_n;
-  // split-K factor: about two CTAs' worth of work per SM (1 CTA/SM resident: 204 KB smem).  Measured: the kernel is
-  // bound by L2->SM bandwidth, not by wave quantisation, so finer splits only add atomics.
+  // split-K factor.  The kernel runs one CTA per SM (204 KB of shared memory), so the grid executes in whole waves of
+  // `sms` CTAs: pick the split that fills 1..3 waves best (ties -> fewer waves: fewer partial sums to add atomically).
+  // Default (HK_WG_SPLIT=0): about two CTAs of work per SM, ignoring the wave boundary; HK_WG_SPLIT=1 selects the wave-aware rule.
+  static int sms = 0, rule = -1;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  if (rule < 0) { const char* v = getenv("HK_WG_SPLIT"); rule = v ? atoi(v) : 0; }
   long long ks = (148 * 2 + out_tiles - 1) / out_tiles;
+  if (rule == 1) {
+    double best = -1.0;
+    for (int w = 1; w <= 3; ++w) {
+      long long k = (long long)sms * w / out_tiles;
+      if (k < 1) k = 1;
+      if (k > total_tiles) k = total_tiles;
+      const long long ctas = k * out_tiles;
+      const long long waves = (ctas + sms - 1) / sms;
+      const double fill = (double)ctas / (double)(waves * sms);
+      if (fill > best + 1e-9) { best = fill; ks = k; }
+    }
+  }
   if (ks > total_tiles) ks = total_tiles;
   if (ks < 1) ks = 1;
   if (ks > 65535) ks = 65535;

@@ -114,11 +114,11 @@ class CrossEntropyLSFn(Function):
         _lib.call('hk_softmax_ce_ls', logits, labels, loss, dlogits, correct, B, K, float(smoothing), 1.0,
                   _lib.stream_ptr())
         ctx.save_for_backward(dlogits)
-        ctx.correct = correct
-        return loss[0]
+        ctx.mark_non_differentiable(correct)
+        return loss[0], correct
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _g_correct=None):
         (dlogits,) = ctx.saved_tensors
         return dlogits * g, None, None
 
@@ -131,7 +131,9 @@ class CrossEntropyLS(torch.nn.Module):
         self.label_smoothing = label_smoothing
 
     def forward(self, logits, labels):
-        return CrossEntropyLSFn.apply(logits, labels, self.label_smoothing)
+        loss, correct = CrossEntropyLSFn.apply(logits, labels, self.label_smoothing)
+        self.last_correct = correct      # [1] int32 on device: top-1 hits of this batch (same kernel, no extra pass)
+        return loss
 
 
 # ----------------------------------------------------------------------------------------------------------

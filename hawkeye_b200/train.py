@@ -21,16 +21,38 @@ from .utils import load_state_dict
 
 
 class AverageMeter:
+    """utils/utils.py:10-26 semantics.  ``update_async`` takes a value that is still on its way from the device (a pinned
+    host scalar + the CUDA event of its copy) so the training loop never blocks on a read-back; ``avg`` drains them."""
+
     def __init__(self):
         self.reset()
 
     def reset(self):
-        self.sum, self.count, self.avg = 0.0, 0, 0.0
+        self.sum, self.count, self._pending = 0.0, 0, []
 
     def update(self, val, n=1):
         self.sum += val * n
         self.count += n
-        self.avg = self.sum / self.count
+
+    def update_async(self, host_buf, index, scale, n, event):
+        self._pending.append((host_buf, index, scale, n, event))
+        self.drain_ready()
+
+    def drain_ready(self):
+        while self._pending and self._pending[0][4].query():       # fold in whatever has already landed
+            self._fold(self._pending.pop(0))
+
+    def _fold(self, item):
+        host_buf, index, scale, n, _ = item
+        self.update(float(host_buf[index]) * scale, n)
+
+    @property
+    def avg(self):
+        while self._pending:
+            item = self._pending.pop(0)
+            item[4].synchronize()
+            self._fold(item)
+        return self.sum / self.count if self.count else 0.0
 
 
 def accuracy(output, target, topk=1):
@@ -67,6 +89,10 @@ class Trainer:
         self.optimizer.grad_scale = 1.0 / self.world
         self.scheduler = self.get_scheduler(self.config.train.scheduler)
         self.average_meters = {'acc': AverageMeter(), 'loss': AverageMeter()}
+        self.copy_stream = torch.cuda.Stream(device=self.device)    # input H2D overlaps the previous step's compute
+        self._readback = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(8)]
+        self._readback_ev = [None] * 8
+        self._readback_i = 0
         if 'resume' in self.config.experiment and self.config.experiment.resume:
             self.load_checkpoint(self.config.experiment.resume)
 
@@ -141,17 +167,53 @@ class Trainer:
         return self.model if model is None else model
 
     # ---- the hot step (train.py:310-325) ------------------------------------------------------------------------
+    def stage_inputs(self, data):
+        """Host -> device copy of one batch on the copy stream (asynchronous for pinned host tensors); the compute stream
+        waits for it in-stream, so the copy of step n+1 overlaps the kernels of step n whenever the host runs ahead."""
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            images = data['img'].to(self.device, non_blocking=True)
+            labels = data['label'].to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        cur.wait_event(ev)
+        for t in (images, labels):
+            if t.is_cuda:
+                t.record_stream(cur)
+        return images, labels
+
     def batch_training(self, data):
-        images, labels = self.to_device(data['img']), self.to_device(data['label'])
+        """train.py:310-325: forward, CE(label_smoothing), zero_grad, backward, (grad all-reduce), step, meters.
+        No host synchronisation: loss and top-1 count are copied back asynchronously every step (8 bytes into pinned
+        memory) and folded into the meters when they have landed."""
+        images, labels = self.stage_inputs(data)
         outputs = self.model(images)
         loss = self.criterion(outputs, labels)
         self.optimizer.zero_grad()
         loss.backward()
         self.allreduce.finish()
         self.optimizer.step()
-        acc = accuracy(outputs, labels, 1)
-        self.average_meters['acc'].update(acc, images.size(0))
-        self.average_meters['loss'].update(loss.item(), images.size(0))
+        n = images.size(0)
+        correct = getattr(self.criterion, 'last_correct', None)
+        if correct is None:                                           # a user-supplied criterion: reference behaviour
+            self.average_meters['acc'].update(accuracy(outputs, labels, 1), n)
+            self.average_meters['loss'].update(loss.item(), n)
+            return loss
+        slot = self._readback_i % len(self._readback)
+        self._readback_i += 1
+        buf = self._readback[slot]
+        if self._readback_ev[slot] is not None:
+            self._readback_ev[slot].synchronize()      # back-pressure: never more than 8 steps of read-backs in flight
+            for m in self.average_meters.values():
+                m.drain_ready()
+        with torch.no_grad():
+            dev = torch.stack((loss.detach().float(), correct[0].float()))
+        buf.copy_(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._readback_ev[slot] = ev
+        self.average_meters['loss'].update_async(buf, 0, 1.0, n, ev)
+        self.average_meters['acc'].update_async(buf, 1, 100.0 / n, n, ev)
         return loss
 
     def batch_validate(self, data):

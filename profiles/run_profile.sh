@@ -13,13 +13,13 @@ python profiles/summarize_launches.py gpurun_out/launches_$R.csv > gpurun_out/la
 for what in "$@"; do
   if [ "$what" = "gram" ]; then
     for B in 32 256; do
-      ncu --set full --clock-control none --import-source on -k regex:"gram_pair|colsum_partial" -c 2 -o gpurun_out/prof_gram_${R}_B$B -f \
+      ncu --set full --clock-control none --import-source on -k regex:"bcnn_gram|gram_pair|colsum_partial" -c 2 -o gpurun_out/prof_gram_${R}_B$B -f \
           python tests/prof_bilinear.py $B > gpurun_out/prof_gram_${R}_B$B.log 2>&1
       ncu -i gpurun_out/prof_gram_${R}_B$B.ncu-rep --page raw --csv > gpurun_out/prof_gram_${R}_B$B.raw.csv 2>/dev/null
     done
   fi
   if [ "$what" = "conv" ]; then
-    ncu --set full --clock-control none --import-source on -k regex:"conv3x3_igemm|conv3x3_wgrad" -s 105 -c 35 -o gpurun_out/prof_conv_$R -f \
+    ncu --set full --clock-control none -k regex:"conv3x3_igemm|conv3x3_wgrad" -s 105 -c 35 -o gpurun_out/prof_conv_$R -f \
         python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/prof_conv_$R.log 2>&1
     ncu -i gpurun_out/prof_conv_$R.ncu-rep --page raw --csv > gpurun_out/prof_conv_$R.raw.csv 2>/dev/null
   fi

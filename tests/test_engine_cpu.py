@@ -78,3 +78,31 @@ def test_flat_params_keep_state_dict_surface():
     flat = engine.FlatParams(m)
     assert list(m.state_dict()) == list(sd) and all(torch.equal(m.state_dict()[k], sd[k]) for k in sd)
     assert flat.numel % 4 == 0 and all(p.data_ptr() % 16 == 0 for p in flat.params)
+
+
+def test_average_meter_async_readback():
+    """Trainer meters fold in device read-backs lazily (no host sync in the step); `.avg` drains what is pending."""
+    import torch
+    from hawkeye_b200.train import AverageMeter
+
+    class Ev:
+        def __init__(self, done):
+            self.done, self.synced = done, False
+
+        def query(self):
+            return self.done
+
+        def synchronize(self):
+            self.done = self.synced = True
+
+    m = AverageMeter()
+    buf = torch.tensor([2.0, 16.0])
+    e1, e2 = Ev(True), Ev(False)
+    m.update_async(buf, 0, 1.0, 4, e1)                  # already landed: folded immediately
+    assert m.count == 4 and abs(m.sum - 8.0) < 1e-9
+    m.update_async(buf, 1, 100.0 / 32, 32, e2)          # still in flight: kept pending
+    assert m.count == 4 and len(m._pending) == 1
+    assert abs(m.avg - (8.0 + 50.0 * 32) / 36) < 1e-9   # .avg waits for it
+    assert e2.synced and not m._pending
+    m.update(1.0, 4)
+    assert m.count == 40
