@@ -215,9 +215,9 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_ma
 // round-to-nearest fp32 -> tf32 (low 13 mantissa bits zero).  tcgen05 kind::tf32 *truncates* its fp32 inputs, so
 // producers round the values they hand to the next MMA; this keeps the TF32 error unbiased.
 __device__ __forceinline__ float tf32_round(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+  // round to nearest, ties away from zero (= cvt.rna.tf32.f32) on the sign-magnitude bit pattern: two integer ops instead
+  // of the NaN/Inf-checked sequence the cvt is expanded to on sm_100a; +-Inf stay Inf, the largest finite values round to Inf.
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 // one lane of a fully converged warp (the MMA warp runs its loop warp-uniformly so descriptor arithmetic stays on the

@@ -687,7 +687,7 @@ int conv3x3_wgrad(const float* x, const float* dy, float* dwp, float* db, int N,
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
-  if (rule < 0) { const char* v = getenv("HK_WG_SPLIT"); rule = v ? atoi(v) : 0; }
+  if (rule < 0) { const char* v = getenv("HK_WG_SPLIT"); rule = v ? atoi(v) : 1; }
   long long ks = (148 * 2 + out_tiles - 1) / out_tiles;
   if (rule == 1) {
     double best = -1.0;

@@ -152,12 +152,31 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const float* Dlb = (epi.D && epi.D_lo) ? epi.D_lo + (long long)bz * epi.strideD : nullptr;
       const float* Eb = epi.E ? epi.E + (long long)bz * epi.strideC : nullptr;
       float* Clb = epi.C_lo ? epi.C_lo + (long long)bz * epi.strideC : nullptr;
+      const bool simple = !Eb && !Db && !Clb && epi.diag == 0.f && !epi.trans_c;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         float v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + set * BN + c * 32, v);
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
+        // fast path (plain scaled store of a full, aligned 32-column chunk): a handful of instructions per element — the
+        // general path below costs ~60 and dominates short-K GEMMs such as the first VGG layer (K = 32)
+        if (simple && row < M && col0 + 32 <= N) {
+          float* dst = Cb + (long long)row * epi.ldc + col0;
+          if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float o = alpha * v[j];
+              if (epi.relu & 1) o = fmaxf(o, 0.f);
+              if (epi.relu & 2) o = tf32_round(o);
+              v[j] = o;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            continue;
+          }
+        }
         if (row < M && col0 < N) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
