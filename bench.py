@@ -24,6 +24,10 @@ import torch  # noqa: E402
 
 K1_FWD_BYTES_PER_IMG = 1449984      # read X 512*196*4 + write Y 512*512*4
 K1_BWD_BYTES_PER_IMG = 1851392
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of bcnn_gram_fwd_kernel from the ncu --set full captures
+# summarised in profiles/gram_r1h_metrics.txt (tests/prof_bilinear.py 32 / 256)
+K1_DRAM_TRAFFIC_B32 = 12.89e6
+K1_DRAM_TRAFFIC_B256 = 102.85e6 + 208.88e6
 VGG16_FWD_GFLOP_PER_IMG = 122.9
 METRIC = '448x448 images/sec, BCNN VGG-16 train step (fwd+CE+bwd+grad all-reduce+SGD), device-timed, max over ranks'
 
@@ -259,12 +263,14 @@ def main():
         return
     hbm_peak, tf_peak, which = measured_peaks()
     if args.no_e2e:
-        t_avg, t256 = float('nan'), float('nan')
+        t_avg, t256, t1024 = float('nan'), float('nan'), float('nan')
     else:
         t_avg = time_bilinear_kernel(32)
         t256 = time_bilinear_kernel(256)
+        t1024 = time_bilinear_kernel(1024)
     ach = 32 * K1_FWD_BYTES_PER_IMG / t_avg / 1e9
     ach256 = 256 * K1_FWD_BYTES_PER_IMG / t256 / 1e9
+    ach1024 = 1024 * K1_FWD_BYTES_PER_IMG / t1024 / 1e9
     flops_img = VGG16_FWD_GFLOP_PER_IMG * (3.0 if args.stage == 2 else 1.0) * 1e9
     conv_tf = flops_img * B * args.steps / (ms * 1e-3) / 1e12
     line = {
@@ -280,10 +286,16 @@ def main():
         'e2e': {'value': e2e, 'unit': 'img/s', 'ms_per_step': ms_e2e / args.steps,
                 'h2d_bytes_per_step': x_host.numel() * 4 + y_host.numel() * 8, 'd2h_bytes_per_step': 8},
         'gpu_launches': launches,
-        'roofline': {'kernel': 'hk_bilinear_pool_fwd (colsum_partial_kernel + gram_pair_kernel<0>), B=32, C=512, HW=196',
+        'roofline': {'kernel': 'hk_bilinear_pool_fwd = bcnn_gram_fwd_kernel<512> (one launch: Gram + sqrt + L2 normalise), '
+                               'B=32 (the per-GPU batch of this workload), C=512, HW=196',
                      'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
-                     'traffic': None, 'peak_source': which, 'us_per_launch': t_avg * 1e6,
-                     'b256': {'achieved': ach256, 'frac': ach256 / hbm_peak, 'us_per_launch': t256 * 1e6}},
+                     'traffic': K1_DRAM_TRAFFIC_B32, 'peak_source': which, 'us_per_launch': t_avg * 1e6,
+                     'algorithmic_bytes_per_launch': 32 * K1_FWD_BYTES_PER_IMG,
+                     'note': 'B=32 moves 46 MB in ~20 us: launch/fill latency bound, and the 33.5 MB output stays in the '
+                             '126 MB L2 (ncu: 12.9 MB of DRAM traffic per launch); the streaming regime is b256/b1024',
+                     'b256': {'achieved': ach256, 'frac': ach256 / hbm_peak, 'us_per_launch': t256 * 1e6,
+                              'traffic': K1_DRAM_TRAFFIC_B256},
+                     'b1024': {'achieved': ach1024, 'frac': ach1024 / hbm_peak, 'us_per_launch': t1024 * 1e6}},
         'roofline_conv': {'bound': 'tensor', 'achieved': conv_tf, 'unit': 'TFLOP/s (tf32, whole step incl. non-conv time)',
                           'peak': tf_peak / 2, 'frac': conv_tf / (tf_peak / 2),
                           'note': 'peak = measured bf16 sustained / 2 (tf32 runs at half the bf16 rate)'},
