@@ -90,6 +90,7 @@ class Trainer:
         self.scheduler = self.get_scheduler(self.config.train.scheduler)
         self.average_meters = {'acc': AverageMeter(), 'loss': AverageMeter()}
         self.copy_stream = torch.cuda.Stream(device=self.device)    # input H2D overlaps the previous step's compute
+        self._in_ring = {}
         self._readback = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(8)]
         self._readback_ev = [None] * 8
         self._readback_i = 0
@@ -168,31 +169,46 @@ class Trainer:
 
     # ---- the hot step (train.py:310-325) ------------------------------------------------------------------------
     def stage_inputs(self, data):
-        """Host -> device copy of one batch on the copy stream (asynchronous for pinned host tensors); the compute stream
-        waits for it in-stream, so the copy of step n+1 overlaps the kernels of step n whenever the host runs ahead."""
+        """Host -> device copy of one batch on the copy stream (asynchronous for pinned host tensors) into a ring of three
+        preallocated device buffers per batch shape — no allocator traffic in the step.  The compute stream waits for the
+        copy in-stream, and the copy stream waits (device-side) until the step that last used the slot has finished, so the
+        copy of step n+1 overlaps the kernels of step n whenever the host runs ahead.  Returns (images, labels, slot)."""
+        img, lab = data['img'], data['label']
+        if img.is_cuda and lab.is_cuda:
+            return img, lab, None
+        key = (tuple(img.shape), img.dtype, tuple(lab.shape), lab.dtype)
+        ring = self._in_ring.get(key)
+        if ring is None:
+            ring = self._in_ring[key] = dict(i=0, slots=[dict(img=torch.empty(img.shape, dtype=img.dtype, device=self.device),
+                                                               lab=torch.empty(lab.shape, dtype=lab.dtype, device=self.device),
+                                                               free=None) for _ in range(3)])
+        slot = ring['slots'][ring['i'] % 3]
+        ring['i'] += 1
         cur = torch.cuda.current_stream()
         with torch.cuda.stream(self.copy_stream):
-            images = data['img'].to(self.device, non_blocking=True)
-            labels = data['label'].to(self.device, non_blocking=True)
+            if slot['free'] is not None:
+                self.copy_stream.wait_event(slot['free'])
+            slot['img'].copy_(img, non_blocking=True)
+            slot['lab'].copy_(lab, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
         cur.wait_event(ev)
-        for t in (images, labels):
-            if t.is_cuda:
-                t.record_stream(cur)
-        return images, labels
+        return slot['img'], slot['lab'], slot
 
     def batch_training(self, data):
         """train.py:310-325: forward, CE(label_smoothing), zero_grad, backward, (grad all-reduce), step, meters.
         No host synchronisation: loss and top-1 count are copied back asynchronously every step (8 bytes into pinned
         memory) and folded into the meters when they have landed."""
-        images, labels = self.stage_inputs(data)
+        images, labels, slot = self.stage_inputs(data)
         outputs = self.model(images)
         loss = self.criterion(outputs, labels)
         self.optimizer.zero_grad()
         loss.backward()
         self.allreduce.finish()
         self.optimizer.step()
+        if slot is not None:                                          # the input slot may be overwritten from here on
+            slot['free'] = torch.cuda.Event()
+            slot['free'].record()
         n = images.size(0)
         correct = getattr(self.criterion, 'last_correct', None)
         if correct is None:                                           # a user-supplied criterion: reference behaviour

@@ -6,7 +6,9 @@
  *     >0 = cudaError_t from a launch.  hk_last_error() gives the text (thread-local).
  *   - the caller owns every device buffer including workspaces (query *_workspace_bytes);
  *     the library allocates nothing and never synchronises; all work is enqueued on `stream`
- *     (a cudaStream_t passed as void*).
+ *     (a cudaStream_t passed as void*).  The only library-owned device state is a 1 MB static table of
+ *     launch-tagged words used by hk_bilinear_pool_fwd for its cross-CTA norm exchange (8 regions handed
+ *     out round-robin per call, so up to 8 calls may be in flight on different streams).
  *   - tensors are contiguous fp32; pointers 16-byte aligned; no CPU fallback: an unsupported
  *     shape is an error (-3), never a silent slow path.
  * Each entry point cites the reference interface it replaces (paths relative to the Hawkeye tree).
