@@ -91,11 +91,6 @@ struct GramArgs {
   const float* s2;
   float* bins;           // mode 2: [B][d] (pre-zeroed)
   int d;
-  // mode 0, fused norm (no K0): every item publishes the sum of its Gram tiles, the items of one image meet on a
-  // self-resetting arrival counter and each derives ||z||^2 = sum_ij G_ij / HW + C^2 eps from the ipi partials.
-  int fused;
-  float* item_sum;       // [B][ipi]  (workspace; written before it is read, no initialisation needed)
-  unsigned int* cnt;     // [B] arrival/departure counters (library-owned, zero between launches)
   int store_mode;        // 0: st.global.cs (streaming)  1: plain st.global
   int x_hint;            // 1: X loads carry an L2 evict_last policy
 };
@@ -224,7 +219,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_pair_kernel(const __grid
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;  // 0..255
-    if (MODE == MODE_BCNN_FWD && !a.fused) asm volatile("griddepcontrol.wait;" ::: "memory");   // K0's channel sums
+    if (MODE == MODE_BCNN_FWD) asm volatile("griddepcontrol.wait;" ::: "memory");   // K0's channel sums
     const size_t CC = (size_t)a.C * a.C;
     int itl = 0, cur_b = -1;
     float inv_norm = 1.f;
@@ -233,7 +228,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_pair_kernel(const __grid
       int blk0, blk1, diag;
       gram_item(it - b * ipi, a.nblk, blk0, blk1, diag);
       const int nacc = blk1 >= 0 ? 2 : 1;
-      if (MODE == MODE_BCNN_FWD && !a.fused && b != cur_b) {
+      if (MODE == MODE_BCNN_FWD && b != cur_b) {
         // closed-form norm from the channel-sum partials (overlaps the TMA/MMA pipeline of this item)
         cur_b = b;
         float acc = 0.f;
@@ -257,50 +252,6 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_pair_kernel(const __grid
       const int set = itl & 1;
       mbar_wait(&acc_full[set], (itl >> 1) & 1);
       tc_fence_after();
-      if (MODE == MODE_BCNN_FWD && a.fused) {
-        // pass 1: sum of this item's Gram entries (the accumulators stay in TMEM for pass 2)
-        float sum = 0.f;
-        for (int ac = 0; ac < nacc; ++ac) {
-#pragma unroll 1
-          for (int c = half * 2; c < half * 2 + 2; ++c) {
-            float v[32];
-            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + set * 256 + ac * 128 + c * 32, v);
-            tmem_ld_wait();
-            float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s4[j & 3] += v[j];
-            sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
-          }
-        }
-        sum = warp_sum(sum);
-        if (lane == 0) red[warp - 2] = sum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et == 0) {
-          float tot = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) tot += red[i];
-          const int t = it - b * ipi;
-          float* ps = a.item_sum + (size_t)b * ipi;
-          ps[t] = tot;
-          unsigned int* cnt = a.cnt + b;
-          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");   // publishes ps[t]
-          unsigned int seen, spins = 0;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
-            if (++spins > HK_SPIN_LIMIT) { printf("hawkeye_b200: gram norm watchdog (item %d)\n", it); __trap(); }
-          } while (seen < (unsigned)ipi);
-          float g = 0.f;
-          for (int i = 0; i < ipi; ++i) g += __ldcg(ps + i);    // fixed order: every item derives the same norm
-          const float nrm = sqrtf(g * a.inv_hw + (float)a.C * (float)a.C * a.eps);
-          const float inn = 1.f / fmaxf(nrm, 1e-12f);
-          red[8] = inn;
-          if (t == 0 && a.inv_norm) a.inv_norm[b] = inn;
-          // departure: the last of the 2*ipi arrivals+departures re-arms the counter for the next launch
-          if (atomicAdd(cnt, 1u) == (unsigned)(2 * ipi - 1)) *cnt = 0u;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        inv_norm = red[8];
-      }
       float craw = 0.f;
       for (int ac = 0; ac < nacc; ++ac) {
         int ablk, bblk;
@@ -386,26 +337,8 @@ static int gram_grid(int total_items) {
   return total_items < sms ? total_items : sms;
 }
 
-// Arrival counters of the fused-norm forward: library-owned (zero-initialised at module load, re-armed by the kernel itself),
-// split into regions handed out round-robin per call so that calls in flight on different streams do not share counters.
 constexpr int GRAM_CNT_REGIONS = 8;
 constexpr int GRAM_CNT_MAXB = 2048;
-__device__ unsigned int g_gram_cnt[GRAM_CNT_REGIONS * GRAM_CNT_MAXB];
-
-static unsigned int* gram_counters() {
-  static std::atomic<unsigned> next{0};
-  static thread_local int dev_cached = -1;
-  static thread_local unsigned int* base = nullptr;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev != dev_cached) {
-    void* p = nullptr;
-    if (cudaGetSymbolAddress(&p, g_gram_cnt) != cudaSuccess) return nullptr;
-    base = static_cast<unsigned int*>(p);
-    dev_cached = dev;
-  }
-  return base + (size_t)(next.fetch_add(1) % GRAM_CNT_REGIONS) * GRAM_CNT_MAXB;
-}
 
 // Tagged tile-sum slots of the single-launch forward: library-owned, zero at module load, never reset (a slot is valid
 // for a launch iff it carries that launch's tag).  Regions are handed out round-robin per call so that calls in flight on
@@ -446,8 +379,7 @@ static int launch_gram(const CUtensorMap& tm, const GramArgs& a, cudaStream_t st
   }
   const int items = a.nblk * (a.nblk - 1) / 2 + (a.nblk + 1) / 2;
   int grid = gram_grid(items * a.B);
-  if (MODE == MODE_BCNN_FWD && a.fused && grid > items) grid = grid / items * items;   // whole images per round
-  if (MODE == MODE_BCNN_FWD && !a.fused) {
+  if (MODE == MODE_BCNN_FWD) {
     // programmatic dependent launch: overlap this kernel's prologue + TMA/MMA pipeline with the channel-sum kernel
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -473,10 +405,10 @@ static int launch_gram(const CUtensorMap& tm, const GramArgs& a, cudaStream_t st
 //   item   = one 128x128 Gram tile (bi <= bj) of one image, ONE accumulator (128 TMEM columns, 4-slot ring):
 //            off-diagonal tiles are computed once and written twice — block (bj,bi) by the transposed, lane-coalesced
 //            direct stores, block (bi,bj) row-major through 128B-swizzled shared memory + TMA bulk-tensor stores;
-//   norm   = ||z||^2 = sum_ij G_ij / HW + C^2 eps.  Every item publishes the sum of its tile (x2 off the diagonal); the
-//            items of an image meet on a self-resetting arrival counter.  The epilogue is software-pipelined: the sum of
-//            item k+1 is published BEFORE item k is normalised and stored, so the cross-CTA latency hides behind a whole
-//            tile of stores and the MMA warp runs up to three tiles ahead.
+//   norm   = ||z||^2 = sum_ij G_ij / HW + C^2 eps.  Every item publishes the sum of its tile (x2 off the diagonal) as one
+//            launch-tagged 64-bit word; a dedicated warp collects the ipi words of the image.  The exchange is software-
+//            pipelined: the sum of item k+1 is published BEFORE item k is normalised and stored, so the cross-CTA latency
+//            hides behind a whole tile of stores and the MMA warp runs up to three tiles ahead.
 // =====================================================================================================================
 constexpr int GF_STAGES = 5;             // shared-memory ring depth allocated (GfArgs::stages of them are used)
 constexpr int GF_SLOTS = 16;              // tagged tile-sum slots per image (>= ipi)
@@ -864,7 +796,7 @@ extern "C" {
 void hk_debug_gram_trace(void* buf) { g_gram_trace = static_cast<unsigned long long*>(buf); }
 
 size_t hk_bilinear_pool_fwd_workspace_bytes(int B, int C, int HW) {
-  // unfused variant: channel-sum partials [B][CS][HW]; fused variants: per-item Gram sums [B][ipi]; + inv_norm [B]
+  // two-kernel version: channel-sum partials [B][CS][HW]; + inv_norm [B] at the end
   const int nblk = C / 128, ipi = nblk * (nblk + 1) / 2;
   const size_t a = (size_t)B * COLSUM_SPLITS * HW, b = (size_t)B * (ipi > 0 ? ipi : 1);
   return ((a > b ? a : b) + B) * sizeof(float);
@@ -881,7 +813,7 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
   float* partial = static_cast<float*>(workspace);
   float* invn_ws = reinterpret_cast<float*>(static_cast<char*>(workspace) + hk_bilinear_pool_fwd_workspace_bytes(B, C, HW)) - B;
   float* invn = inv_norm_out ? inv_norm_out : invn_ws;
-  // 0: K0 channel sums + PDL (first version), 1: fused norm on the tile-pair kernel, 2: single-tile items, pipelined norm
+  // HK_GRAM_FUSED=0 forces the two-kernel version (A/B measurements); default: the single-launch kernel when it applies
   const int variant = env_int("HK_GRAM_FUSED", 2);
   const int store_mode = env_int("HK_GRAM_STORE", 1);
   const int x_hint = env_int("HK_GRAM_XHINT", 1);
@@ -935,31 +867,15 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
     }
     return 0;
   }
-  const int ipi = a.nblk * (a.nblk - 1) / 2 + (a.nblk + 1) / 2;
-  if (!variant || ipi > 148) {
-    CUtensorMap tm;
-    if ((r = make_x_map(&tm, x, B, C, HW))) return r;
-    colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, colsum_smem(HW), stream>>>(x, partial, C, HW, COLSUM_SPLITS, nullptr, nullptr, 0);
-    HK_LAUNCH_CHECK("colsum_partial_kernel");
-    a.B = B; a.partial = partial; a.CS = COLSUM_SPLITS;
-    a.Y = y; a.inv_norm = invn;
-    return launch_gram<MODE_BCNN_FWD>(tm, a, stream);
-  }
-  // fused: one launch per <= GRAM_CNT_MAXB images
-  a.fused = 1;
-  for (int b0 = 0; b0 < B; b0 += GRAM_CNT_MAXB) {
-    const int nb = B - b0 < GRAM_CNT_MAXB ? B - b0 : GRAM_CNT_MAXB;
-    CUtensorMap tm;
-    if ((r = make_x_map(&tm, x + (size_t)b0 * C * HW, nb, C, HW))) return r;
-    a.B = nb;
-    a.Y = y + (size_t)b0 * C * C;
-    a.inv_norm = invn + b0;
-    a.item_sum = partial + (size_t)b0 * ipi;
-    a.cnt = gram_counters();
-    HK_REQUIRE(a.cnt, HK_ERR_DRIVER, "hk_bilinear_pool_fwd: counter symbol not resolvable");
-    if ((r = launch_gram<MODE_BCNN_FWD>(tm, a, stream))) return r;
-  }
-  return 0;
+  // general C (more than GF_SLOTS tiles per image) or HK_GRAM_FUSED=0: channel-sum pre-kernel + tile-pair Gram kernel,
+  // overlapped by programmatic dependent launch (the first version of this op)
+  CUtensorMap tm;
+  if ((r = make_x_map(&tm, x, B, C, HW))) return r;
+  colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, colsum_smem(HW), stream>>>(x, partial, C, HW, COLSUM_SPLITS, nullptr, nullptr, 0);
+  HK_LAUNCH_CHECK("colsum_partial_kernel");
+  a.B = B; a.partial = partial; a.CS = COLSUM_SPLITS;
+  a.Y = y; a.inv_norm = invn;
+  return launch_gram<MODE_BCNN_FWD>(tm, a, stream);
 }
 
 size_t hk_bilinear_pool_bwd_workspace_bytes(int B, int C, int HW) {

@@ -27,9 +27,8 @@ def check(B=4):
 
 
 def main():
-    variants = [dict(HK_GRAM_FUSED='0'), dict(HK_GRAM_FUSED='1'), dict(HK_GRAM_FUSED='2'),
-                dict(HK_GRAM_FUSED='2', HK_GRAM_STORE='1'), dict(HK_GRAM_FUSED='2', HK_GRAM_XHINT='0'),
-                dict(HK_GRAM_FUSED='2', HK_GRAM_STORE='1', HK_GRAM_XHINT='0')]
+    variants = [dict(HK_GRAM_FUSED='0'), dict(HK_GRAM_FUSED='2'), dict(HK_GRAM_FUSED='2', HK_GRAM_STORE='0'),
+                dict(HK_GRAM_FUSED='2', HK_GRAM_STAGES='4'), dict(HK_GRAM_FUSED='2', HK_GRAM_PDL='0')]
     if len(sys.argv) > 1:
         variants = [dict(kv.split('=') for kv in a.split(',')) for a in sys.argv[1:]]
     out = []

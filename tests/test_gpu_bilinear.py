@@ -34,7 +34,7 @@ def test_full_size_golden(golden):
     assert e < 2e-3
 
 
-@pytest.mark.parametrize('B,C,H,W', [(3, 512, 14, 14), (2, 256, 8, 8), (5, 128, 6, 6), (2, 384, 14, 14)])
+@pytest.mark.parametrize('B,C,H,W', [(3, 512, 14, 14), (2, 256, 8, 8), (5, 128, 6, 6), (2, 384, 14, 14), (2, 768, 4, 4)])
 def test_vs_oracle(B, C, H, W):
     from hawkeye_b200 import ops
     from oracle import hop_oracle as O
