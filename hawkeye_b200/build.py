@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f'nvcc failed on {s}')
-    cmd = [NVCC, '-shared', '-o', OUT] + objs + ['-lcudart']
+    cmd = [NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', OUT] + objs + ['-lcudart']
     subprocess.check_call(cmd)
     return OUT
 
