@@ -413,7 +413,8 @@ static int launch_gram(const CUtensorMap& tm, const GramArgs& a, cudaStream_t st
 constexpr int GF_STAGES = 5;             // shared-memory ring depth allocated (GfArgs::stages of them are used)
 constexpr int GF_SLOTS = 16;              // tagged tile-sum slots per image (>= ipi)
 constexpr int GF_OUT_BYTES = 128 * 128;   // one 128-row x 32-column fp32 box
-constexpr int GF_SMEM = GF_STAGES * GRAM_STAGE_BYTES + 4 * GF_OUT_BYTES + 1024 + 512;
+constexpr int GF_MAX_ITEMS = 384;         // items per CTA per launch (GRAM_CNT_MAXB images x <= 16 tiles over >= 148 CTAs, with slack)
+constexpr int GF_SMEM = GF_STAGES * GRAM_STAGE_BYTES + 4 * GF_OUT_BYTES + 1024 + 512 + 2 * GF_MAX_ITEMS;
 
 struct GfArgs {
   int B, C, HW, nblk;
@@ -427,6 +428,7 @@ struct GfArgs {
   unsigned long long* trace;   // profiling only: [grid][16] globaltimer stamps (hk_debug_gram_trace), or null
   int stages;                  // 2..GF_STAGES
   int pdl;                     // launched with programmatic stream serialization
+  int balance;                 // 1: units-balanced item schedule (see the kernel prologue), 0: plain round-robin
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -480,13 +482,14 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(norm_ready + 4);
   float* sum_part = reinterpret_cast<float*>(tmem_slot + 2);   // [4][8]
   float* inv_box = sum_part + 32;                              // [4]
+  int* n_my_box = reinterpret_cast<int*>(inv_box + 4);
+  uint16_t* sched = reinterpret_cast<uint16_t*>(n_my_box + 1);  // [GF_MAX_ITEMS] item ids (b * ipi + t) of this CTA, in order
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = CT ? CT : a.C;
   const int ipi = a.nblk * (a.nblk + 1) / 2;     // items (tiles bi <= bj) per image
   const int total_items = a.B * ipi;
   const int nk = (a.HW + 31) / 32;
-  const int n_my = (int)blockIdx.x < total_items ? (total_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -498,11 +501,54 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
     fence_barrier_init();
   }
+  if (warp == 2 && lane == 0) {
+    // Item schedule of this CTA.  Off-diagonal tiles cost two output blocks, diagonal tiles one: off-diagonal items go
+    // round-robin over the G CTAs; diagonal items first top up the CTAs that got one off-diagonal item fewer (two each),
+    // then continue round-robin (longest-processing-time-first for two job sizes).  Each CTA walks its items in image order,
+    // so the tiles of an image are in flight at the same time on all its CTAs and dependencies only point to earlier images.
+    const int G = gridDim.x, c = blockIdx.x;
+    const int n_off = a.nblk * (a.nblk - 1) / 2;
+    const int O = a.B * n_off, D = a.B * a.nblk;
+    const int r = O % G, L = G - r;
+    const int END = 0x7fffffff;
+    int oi = c < O ? c : END;
+    int dj = END;
+    if (a.balance) {
+      if (c >= r && c - r < 2 * L && c - r < D) dj = c - r;
+      else if (2 * L + c < D) dj = 2 * L + c;
+    } else {
+      oi = END;       // plain round-robin over the image-major item list
+    }
+    int n = 0;
+    if (a.balance) {
+      while ((oi != END || dj != END) && n < GF_MAX_ITEMS) {
+        const int bo = oi != END ? oi / n_off : END, bd = dj != END ? dj / a.nblk : END;
+        if (bo <= bd) {
+          sched[n++] = (uint16_t)(bo * ipi + (oi - bo * n_off));
+          oi = oi + G < O ? oi + G : END;
+        } else {
+          sched[n++] = (uint16_t)(bd * ipi + n_off + (dj - bd * a.nblk));
+          int nx;
+          if (dj < 2 * L) {
+            nx = dj + L;
+            if (nx >= 2 * L) nx = 2 * L + c;
+          } else {
+            nx = dj + G;
+          }
+          dj = nx < D ? nx : END;
+        }
+      }
+    } else {
+      for (int it = c; it < total_items && n < GF_MAX_ITEMS; it += G) sched[n++] = (uint16_t)it;
+    }
+    *n_my_box = n;
+  }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int n_my = *n_my_box;
   if (a.pdl) {
     // programmatic dependent launch: the next grid may begin its prologue as soon as every CTA of this one got here; this
     // grid must not touch global memory before its predecessor has completed and flushed.
@@ -517,7 +563,8 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       uint64_t policy;
       asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
       int kbg = 0;
-      for (int it = blockIdx.x; it < total_items && !(a.dbg & 8); it += gridDim.x) {
+      for (int k = 0; k < n_my && !(a.dbg & 8); ++k) {
+        const int it = sched[k];
         const int b = it / ipi;
         int bi, bj;
         gf_item(it - b * ipi, a.nblk, bi, bj);
@@ -541,7 +588,8 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint32_t idesc = make_idesc_tf32(128, 128, 0, 0);
     const uint64_t desc_tmpl = make_sdesc(0, 16, 1024);
     int kbg = 0, itl = 0;
-    for (int it = blockIdx.x; it < total_items && !(a.dbg & 8); it += gridDim.x, ++itl) {
+    for (; itl < n_my && !(a.dbg & 8); ++itl) {
+      const int it = sched[itl];
       const int b = it / ipi;
       int bi, bj;
       gf_item(it - b * ipi, a.nblk, bi, bj);
@@ -577,7 +625,7 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     //             values with a fixed shuffle tree (every CTA derives the identical norm), hand 1/||z|| to the epilogue.
     // publish(k+1) precedes resolve(k): the cross-CTA latency hides behind one whole tile of stores.
     auto publish = [&](int k) {
-      const int it = blockIdx.x + k * gridDim.x;
+      const int it = sched[k];
       const int b = it / ipi, t = it - b * ipi;
       int bi, bj;
       gf_item(t, a.nblk, bi, bj);
@@ -595,7 +643,7 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (n_my > 0) publish(0);
     for (int k = 0; k < n_my; ++k) {
       if (k + 1 < n_my) publish(k + 1);
-      const int it = blockIdx.x + k * gridDim.x;
+      const int it = sched[k];
       const int b = it / ipi, t = it - b * ipi;
       const unsigned long long* ps = a.slots + (size_t)b * GF_SLOTS;
       unsigned long long w = 0;
@@ -656,7 +704,7 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (n_my > 0) tile_sum(0);
     for (int k = 0; k < n_my; ++k) {
       if (k + 1 < n_my) tile_sum(k + 1);
-      const int it = blockIdx.x + k * gridDim.x;
+      const int it = sched[k];
       const int b = it / ipi, t = it - b * ipi;
       int bi, bj;
       gf_item(t, a.nblk, bi, bj);
@@ -839,6 +887,7 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
     if (g.stages < 2) g.stages = 2;
     if (g.stages > GF_STAGES) g.stages = GF_STAGES;
     g.pdl = env_int("HK_GRAM_PDL", 1);
+    const int balance_env = env_int("HK_GRAM_BALANCE", -1);     // -1: automatic (below), 0/1: forced (A/B measurements)
     for (int b0 = 0; b0 < B; b0 += GRAM_CNT_MAXB) {
       const int nb = B - b0 < GRAM_CNT_MAXB ? B - b0 : GRAM_CNT_MAXB;
       CUtensorMap tmx, tmy;
@@ -850,6 +899,11 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
       g.slots = gram_slots(&g.tag);
       HK_REQUIRE(g.slots, HK_ERR_DRIVER, "hk_bilinear_pool_fwd: slot symbol not resolvable");
       const int grid = gram_grid(nb * ipi3);
+      // units-balanced schedule only while the launch is a few waves long (B=32: 19.3 vs 21.8 us); for long launches the
+      // plain image-major round-robin keeps the tiles of an image closer in time (B=1024: 302 vs 325 us)
+      g.balance = balance_env >= 0 ? balance_env : (nb * ipi3 <= 3 * grid ? 1 : 0);
+      HK_REQUIRE((nb * ipi3 + grid - 1) / grid + 8 <= GF_MAX_ITEMS && nb * ipi3 <= 65535, HK_ERR_UNSUPPORTED,
+                 "hk_bilinear_pool_fwd: item schedule does not fit (B=%d C=%d)", nb, C);
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(grid);
       cfg.blockDim = dim3(GF_THREADS);

@@ -33,7 +33,7 @@ def main():
         variants = [dict(kv.split('=') for kv in a.split(',')) for a in sys.argv[1:]]
     out = []
     for v in variants:
-        for k in ('HK_GRAM_FUSED', 'HK_GRAM_STORE', 'HK_GRAM_XHINT', 'HK_GRAM_DBG', 'HK_GRAM_STAGES', 'HK_GRAM_PDL', 'HK_GRAM_PAIR'):
+        for k in ('HK_GRAM_FUSED', 'HK_GRAM_STORE', 'HK_GRAM_XHINT', 'HK_GRAM_DBG', 'HK_GRAM_STAGES', 'HK_GRAM_PDL', 'HK_GRAM_BALANCE'):
             os.environ.pop(k, None)
         os.environ.update(v)
         r = dict(variant=v, rel_err=check())
@@ -43,7 +43,7 @@ def main():
                               frac=round(B * bench.K1_FWD_BYTES_PER_IMG / t / 1e9 / peak, 4))
         print(json.dumps(r), flush=True)
         out.append(r)
-    for k in ('HK_GRAM_FUSED', 'HK_GRAM_STORE', 'HK_GRAM_XHINT', 'HK_GRAM_DBG', 'HK_GRAM_STAGES', 'HK_GRAM_PDL', 'HK_GRAM_PAIR'):
+    for k in ('HK_GRAM_FUSED', 'HK_GRAM_STORE', 'HK_GRAM_XHINT', 'HK_GRAM_DBG', 'HK_GRAM_STAGES', 'HK_GRAM_PDL', 'HK_GRAM_BALANCE'):
         os.environ.pop(k, None)
     # backward (two kernels + GEMM), same protocol
     for B in (32, 256):
