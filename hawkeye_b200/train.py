@@ -312,6 +312,50 @@ class Trainer:
         pass
 
 
+class PeerLearningTrainer(Trainer):
+    """Examples/PeerLearning.py:17-111 on this Trainer: PeerLearningNet (two base models) + the co-teaching loss with the
+    drop-rate ramp of Eqn.(2) (0 -> ``model.drop_rate`` over the first ``model.T_k`` epochs).  Model and loss are parity-tested
+    against the reference on CPU (tests/test_peer_learning.py); each base model is the registry's native BCNN / CBCNN / MPN."""
+
+    def __init__(self, config=None, dataloaders=None):
+        super().__init__(config, dataloaders)
+        import numpy as np
+        mc = self.config.model
+        self.rate_scheduler = np.ones(self.total_epoch) * mc.drop_rate                  # Examples/PeerLearning.py:21-24
+        self.rate_scheduler[:mc.T_k] = np.linspace(0, mc.drop_rate, mc.T_k)[:self.total_epoch]
+        self.average_meters = {k: AverageMeter() for k in ('acc', 'acc1', 'acc2', 'loss1', 'loss2')}
+
+    def get_criterion(self, config):
+        from .losses import peer_learning_loss
+        return peer_learning_loss
+
+    def batch_training(self, data):
+        images, labels, slot = self.stage_inputs(data)
+        logits1, logits2 = self.model(images)
+        loss1, loss2 = self.criterion(logits1, logits2, labels, drop_rate=float(self.rate_scheduler[self.epoch]))
+        self.optimizer.zero_grad()
+        loss1.backward()
+        loss2.backward()
+        self.allreduce.finish()
+        self.optimizer.step()
+        if slot is not None:
+            slot['free'] = torch.cuda.Event()
+            slot['free'].record()
+        n = images.size(0)
+        acc1, acc2 = accuracy(logits1, labels, 1), accuracy(logits2, labels, 1)
+        for k, v in (('acc', max(acc1, acc2)), ('acc1', acc1), ('acc2', acc2), ('loss1', loss1.item()), ('loss2', loss2.item())):
+            self.average_meters[k].update(v, n)
+        return loss1, loss2
+
+    def batch_validate(self, data):
+        images, labels = self.to_device(data['img']), self.to_device(data['label'])
+        with torch.no_grad():
+            logits1, logits2 = self.model(images)
+        acc1, acc2 = accuracy(logits1, labels, 1), accuracy(logits2, labels, 1)
+        for k, v in (('acc', max(acc1, acc2)), ('acc1', acc1), ('acc2', acc2)):
+            self.average_meters[k].update(v, images.size(0))
+
+
 class _Plateau:
     """ReduceLROnPlateau(mode='max') over FusedSGD/FusedAdam param_groups (Examples/BCNN.py:42-48)."""
 
