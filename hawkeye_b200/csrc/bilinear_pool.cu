@@ -458,12 +458,6 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// positive finite values only (sqrt outputs): round-to-nearest fp32 -> tf32 in two integer ops (cvt.rna.tf32.f32 is
-// emulated with a NaN/Inf check on sm_100a; ties differ only in the direction of exact halves)
-__device__ __forceinline__ float tf32_round_pos(float x) {
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
-}
-
 constexpr int GF_THREADS = 352;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 norm exchange
 
 // CT: compile-time C (row pitch of Y in floats) so the 32 transposed stores of a chunk use immediate offsets; 0 = runtime C.
@@ -723,7 +717,7 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * 128 + c * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = tf32_round_pos(fast_sqrt(fmaf(v[j], a.inv_hw, a.eps)) * inv_norm);
+        for (int j = 0; j < 32; ++j) v[j] = tf32_round(fast_sqrt(fmaf(v[j], a.inv_hw, a.eps)) * inv_norm);
         // block (bj, bi): transposed — lanes run along a row of Y
         float* y = a.Y + (size_t)b * CC + (size_t)(bj * 128 + c * 32) * C + bi * 128 + r;
         if (a.dbg & 1) {
