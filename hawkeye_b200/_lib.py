@@ -97,6 +97,15 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+def set_precise(on):
+    """Process-wide precision mode of the library: False = single-pass TF32 (default), True = 3xTF32 (parity runs)."""
+    lib().hk_set_precise(1 if on else 0)
+
+
+def get_precise():
+    return bool(lib().hk_get_precise())
+
+
 def launch_count():
     return int(lib().hk_launch_count())
 

@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "host.h"
+#include "gemm.h"
 #include "../../include/hawkeye_b200.h"
 
 namespace hk {
@@ -34,7 +35,7 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 // ---------------------------------------------------------------- K0: per-location channel-sum partials
 // partial[b][cs][p] = sum_{c in split cs} x[b][c][p];  also zeroes the per-image scalars used by the backward.
 __global__ void colsum_partial_kernel(const float* __restrict__ X, float* __restrict__ partial, int C, int HW, int CS,
-                                      float* zero_a, float* zero_b, int zero_n) {
+                                      float* zero_a, float* zero_b, int zero_n, unsigned keep_mask = 0xffffe000u) {
   // let the dependent Gram kernel (launched with programmatic stream serialization) start its TMA/MMA pipeline now;
   // it only needs our result in its epilogue (griddepcontrol.wait there).
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -57,10 +58,10 @@ __global__ void colsum_partial_kernel(const float* __restrict__ X, float* __rest
       for (int c = c0 + rl; c < c1; c += nrl) {
         // sum what the tensor core will see: kind::tf32 truncates the low 13 mantissa bits
         const float4 v = __ldg(xb + (size_t)c * Q + q);
-        s.x += __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-        s.y += __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-        s.z += __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-        s.w += __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        s.x += __uint_as_float(__float_as_uint(v.x) & keep_mask);
+        s.y += __uint_as_float(__float_as_uint(v.y) & keep_mask);
+        s.z += __uint_as_float(__float_as_uint(v.z) & keep_mask);
+        s.w += __uint_as_float(__float_as_uint(v.w) & keep_mask);
       }
       reinterpret_cast<float4*>(red + (size_t)rl * HW)[q] = s;
     }
@@ -762,6 +763,64 @@ bcnn_gram_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------- precise mode (3xTF32 Gram from the generic GEMM)
+// y (holding the raw Gram G = X X^T) -> normalize(sqrt(G/HW + eps)); one block per image.
+__global__ void bilinear_finish_kernel(float* __restrict__ y, float* __restrict__ inv_norm_out, int CC, float inv_hw,
+                                       float eps) {
+  __shared__ float red[32];
+  float* yb = y + (size_t)blockIdx.x * CC;
+  float acc = 0.f;
+  for (int e = threadIdx.x; e < CC; e += blockDim.x) acc += fmaf(yb[e], inv_hw, eps);     // z^2
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+  const float inv = 1.f / fmaxf(sqrtf(t), 1e-12f);
+  for (int e = threadIdx.x; e < CC; e += blockDim.x) yb[e] = sqrtf(fmaf(yb[e], inv_hw, eps)) * inv;
+  if (threadIdx.x == 0 && inv_norm_out) inv_norm_out[blockIdx.x] = inv;
+}
+// S (holding the raw Gram) -> S[i][j] = (dY[i][j] + dY[j][i]) / (2 z_ij);  inv_norm[b] = 1/||z||, c_raw[b] = <dY, z>
+__global__ void bilinear_bwd_s_kernel(float* __restrict__ S, const float* __restrict__ dY, float* __restrict__ inv_norm,
+                                      float* __restrict__ c_raw, int C, float inv_hw, float eps) {
+  __shared__ float red[2][32];
+  const size_t CC = (size_t)C * C;
+  float* Sb = S + blockIdx.x * CC;
+  const float* dyb = dY + blockIdx.x * CC;
+  float n2 = 0.f, cr = 0.f;
+  for (size_t e = threadIdx.x; e < CC; e += blockDim.x) {
+    const int i = (int)(e / C), j = (int)(e % C);
+    const float z2 = fmaf(Sb[e], inv_hw, eps);
+    const float z = sqrtf(z2);
+    const float d = dyb[e];
+    n2 += z2;
+    cr = fmaf(d, z, cr);
+    Sb[e] = (d + dyb[(size_t)j * C + i]) / (2.f * z);
+  }
+  n2 = warp_sum(n2); cr = warp_sum(cr);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = n2; red[1][threadIdx.x >> 5] = cr; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; b += red[1][i]; }
+    inv_norm[blockIdx.x] = 1.f / fmaxf(sqrtf(a), 1e-12f);
+    c_raw[blockIdx.x] = b;
+  }
+}
+// bins[b][(h1[i]+h2[j]) mod d] += s1[i] s2[j] G[b][i][j]
+__global__ void cbp_scatter_kernel(const float* __restrict__ G, const int* __restrict__ h1, const int* __restrict__ h2,
+                                   const float* __restrict__ s1, const float* __restrict__ s2, float* __restrict__ bins,
+                                   int C, int d) {
+  const int b = blockIdx.y;
+  const size_t n = (size_t)C * C;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / C), j = (int)(e % C);
+    int k = h1[i] + h2[j];
+    if (k >= d) k -= d;
+    atomicAdd(&bins[(size_t)b * d + k], s1[i] * s2[j] * G[(size_t)b * n + e]);
+  }
+}
+
 static int make_y_map(CUtensorMap* tm, const float* Y, int B, int C) {
   uint64_t dims[3] = {(uint64_t)C, (uint64_t)C, (uint64_t)B};
   uint64_t strides[2] = {(uint64_t)C * 4, (uint64_t)C * C * 4};
@@ -825,9 +884,6 @@ __global__ void norm_from_s_kernel(const float* s, float* inv_norm, int C, int H
   }
 }
 
-int gemm_tf32(const float* A, int a_mn, long long lda, long long strideA, const float* B, int b_mn, long long ldb,
-              long long strideB, const struct GemmEpi& epi, int M, int N, int K, int batch, cudaStream_t stream);
-
 }  // namespace hk
 
 using namespace hk;
@@ -855,6 +911,14 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
   float* partial = static_cast<float*>(workspace);
   float* invn_ws = reinterpret_cast<float*>(static_cast<char*>(workspace) + hk_bilinear_pool_fwd_workspace_bytes(B, C, HW)) - B;
   float* invn = inv_norm_out ? inv_norm_out : invn_ws;
+  if (precise()) {   // 3xTF32 Gram on the generic GEMM, then sqrt + L2 normalise in place; nothing rounded
+    GemmEpi e = {};
+    e.C = y; e.ldc = C; e.strideC = (long long)C * C; e.alpha = 1.f;
+    if ((r = gemm_tf32(x, 0, HW, (long long)C * HW, x, 0, HW, (long long)C * HW, e, C, C, HW, B, stream))) return r;
+    bilinear_finish_kernel<<<B, 1024, 0, stream>>>(y, invn, C * C, 1.f / (float)HW, 1e-5f);
+    HK_LAUNCH_CHECK("bilinear_finish_kernel");
+    return 0;
+  }
   // HK_GRAM_FUSED=0 forces the two-kernel version (A/B measurements); default: the single-launch kernel when it applies
   const int variant = env_int("HK_GRAM_FUSED", 2);
   const int store_mode = env_int("HK_GRAM_STORE", 1);
@@ -946,6 +1010,22 @@ int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int 
   float* craw = invn + B;
   float* alpha = craw + B;
   float* beta = alpha + B;
+  if (precise()) {
+    colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, colsum_smem(HW), stream>>>(x, partial, C, HW, COLSUM_SPLITS, nullptr,
+                                                                                  nullptr, 0, 0xffffffffu);
+    HK_LAUNCH_CHECK("colsum_partial_kernel");
+    colsum_finish_kernel<<<B, 256, 0, stream>>>(partial, svec, COLSUM_SPLITS, HW);
+    HK_LAUNCH_CHECK("colsum_finish_kernel");
+    GemmEpi e = {};
+    e.C = S; e.ldc = C; e.strideC = (long long)C * C; e.alpha = 1.f;
+    if ((r = gemm_tf32(x, 0, HW, (long long)C * HW, x, 0, HW, (long long)C * HW, e, C, C, HW, B, stream))) return r;
+    bilinear_bwd_s_kernel<<<B, 1024, 0, stream>>>(S, dy, invn, craw, C, 1.f / (float)HW, 1e-5f);
+    HK_LAUNCH_CHECK("bilinear_bwd_s_kernel");
+    bilinear_bwd_scalars_kernel<<<(B + 127) / 128, 128, 0, stream>>>(invn, craw, 1.f / (float)HW, alpha, beta, B);
+    HK_LAUNCH_CHECK("bilinear_bwd_scalars_kernel");
+    return hk_gemm_tf32(S, 0, C, (long long)C * C, x, 1, HW, (long long)C * HW, dx, HW, (long long)C * HW, 0, C, HW, C, B,
+                        1.f, alpha, 0.f, svec, 0, HW, 1.f, beta, 0, stream_);
+  }
   CUtensorMap tm;
   if ((r = make_x_map(&tm, x, B, C, HW))) return r;
   colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, colsum_smem(HW), stream>>>(x, partial, C, HW, COLSUM_SPLITS, craw, nullptr, 1);
@@ -962,9 +1042,10 @@ int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int 
   HK_LAUNCH_CHECK("norm_from_s_kernel");
   bilinear_bwd_scalars_kernel<<<(B + 127) / 128, 128, 0, stream>>>(invn, craw, 1.f / (float)HW, alpha, beta, B);
   HK_LAUNCH_CHECK("bilinear_bwd_scalars_kernel");
-  // dX = alpha_b * (S . X) + beta_b * 1 s^T      (M=C, K=C, N=HW; X is the MN-major B operand)
+  // dX = alpha_b * (S . X) + beta_b * 1 s^T      (M=C, K=C, N=HW; X is the MN-major B operand); rounded to tf32: it is
+  // the dY operand of the last conv's dgrad / wgrad MMAs
   return hk_gemm_tf32(S, 0, C, (long long)C * C, x, 1, HW, (long long)C * HW, dx, HW, (long long)C * HW, 0, C, HW, C, B,
-                      1.f, alpha, 0.f, svec, 0, HW, 1.f, beta, 0, stream_);
+                      1.f, alpha, 0.f, svec, 0, HW, 1.f, beta, 2, stream_);
 }
 
 }  // extern "C"
@@ -990,7 +1071,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 }
 
 // y = normalize(sign(pre) * sqrt(|pre| + 1e-10)); one block per image
-__global__ void cbp_finalize_fwd_kernel(const float* __restrict__ pre, float* __restrict__ y, int d) {
+__global__ void cbp_finalize_fwd_kernel(const float* __restrict__ pre, float* __restrict__ y, int d, int round) {
   __shared__ float red[32];
   const float* p = pre + (size_t)blockIdx.x * d;
   float acc = 0.f;
@@ -1003,7 +1084,7 @@ __global__ void cbp_finalize_fwd_kernel(const float* __restrict__ pre, float* __
   for (int k = threadIdx.x; k < d; k += blockDim.x) {
     const float v = p[k];
     const float s = (v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f)) * sqrtf(fabsf(v) + 1e-10f);
-    y[(size_t)blockIdx.x * d + k] = tf32_round(s * inv);
+    y[(size_t)blockIdx.x * d + k] = round ? tf32_round(s * inv) : s * inv;
   }
 }
 
@@ -1042,7 +1123,7 @@ __global__ void cbp_finalize_bwd_kernel(const float* __restrict__ pre, const flo
 // S[b][i][j] = dG[i][j] + dG[j][i],  dG[i][j] = s1[i] s2[j] dpre[b][(h1[i]+h2[j]) mod d]
 __global__ void cbp_build_s_kernel(const float* __restrict__ dpre, const int* __restrict__ h1,
                                    const int* __restrict__ h2, const float* __restrict__ s1,
-                                   const float* __restrict__ s2, float* __restrict__ S, int C, int d) {
+                                   const float* __restrict__ s2, float* __restrict__ S, int C, int d, int round) {
   const int b = blockIdx.y;
   const float* dp = dpre + (size_t)b * d;
   const size_t n = (size_t)C * C;
@@ -1052,7 +1133,8 @@ __global__ void cbp_build_s_kernel(const float* __restrict__ dpre, const int* __
     if (k1 >= d) k1 -= d;
     int k2 = h1[j] + h2[i];
     if (k2 >= d) k2 -= d;
-    S[(size_t)b * n + e] = tf32_round(s1[i] * s2[j] * dp[k1] + s1[j] * s2[i] * dp[k2]);
+    const float v = s1[i] * s2[j] * dp[k1] + s1[j] * s2[i] * dp[k2];
+    S[(size_t)b * n + e] = round ? tf32_round(v) : v;
   }
 }
 
@@ -1068,6 +1150,18 @@ int hk_cbp_fwd(const float* x, const int* h1, const int* h2, const float* s1, co
   HK_REQUIRE(h1 && h2 && s1 && s2 && y && pre && d > 0, HK_ERR_ARG, "hk_cbp_fwd: null pointer / bad d");
   cudaError_t e = cudaMemsetAsync(pre, 0, (size_t)B * d * sizeof(float), stream);
   if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(pre): %s", cudaGetErrorString(e));
+  if (precise()) {   // 3xTF32 Gram on the generic GEMM, scattered into the bins by a plain kernel
+    Scratch g((size_t)B * C * C * sizeof(float), stream);
+    HK_REQUIRE(g.p, HK_ERR_DRIVER, "hk_cbp_fwd (precise): cudaMallocAsync failed");
+    GemmEpi ge = {};
+    ge.C = g.f(); ge.ldc = C; ge.strideC = (long long)C * C; ge.alpha = 1.f;
+    if ((r = gemm_tf32(x, 0, HW, (long long)C * HW, x, 0, HW, (long long)C * HW, ge, C, C, HW, B, stream))) return r;
+    cbp_scatter_kernel<<<dim3(148, B), 256, 0, stream>>>(g.f(), h1, h2, s1, s2, pre, C, d);
+    HK_LAUNCH_CHECK("cbp_scatter_kernel");
+    cbp_finalize_fwd_kernel<<<B, 256, 0, stream>>>(pre, y, d, 0);
+    HK_LAUNCH_CHECK("cbp_finalize_fwd_kernel");
+    return 0;
+  }
   CUtensorMap tm;
   if ((r = make_x_map(&tm, x, B, C, HW))) return r;
   GramArgs a = {};
@@ -1075,7 +1169,7 @@ int hk_cbp_fwd(const float* x, const int* h1, const int* h2, const float* s1, co
   a.inv_hw = 1.f; a.eps = 0.f;
   a.h1 = h1; a.h2 = h2; a.s1 = s1; a.s2 = s2; a.bins = pre; a.d = d;
   if ((r = launch_gram<MODE_CBP_FWD>(tm, a, stream))) return r;
-  cbp_finalize_fwd_kernel<<<B, 256, 0, stream>>>(pre, y, d);
+  cbp_finalize_fwd_kernel<<<B, 256, 0, stream>>>(pre, y, d, 1);
   HK_LAUNCH_CHECK("cbp_finalize_fwd_kernel");
   return 0;
 }
@@ -1095,11 +1189,11 @@ int hk_cbp_bwd(const float* x, const float* pre, const float* dy, const int* h1,
   float* dpre = S + (size_t)B * C * C;
   cbp_finalize_bwd_kernel<<<B, 256, 0, stream>>>(pre, dy, dpre, d);
   HK_LAUNCH_CHECK("cbp_finalize_bwd_kernel");
-  cbp_build_s_kernel<<<dim3(148, B), 256, 0, stream>>>(dpre, h1, h2, s1, s2, S, C, d);
+  cbp_build_s_kernel<<<dim3(148, B), 256, 0, stream>>>(dpre, h1, h2, s1, s2, S, C, d, precise() ? 0 : 1);
   HK_LAUNCH_CHECK("cbp_build_s_kernel");
   // dX = (dG + dG^T) . X      (M = C, K = C, N = HW; X is the MN-major B operand)
   return hk_gemm_tf32(S, 0, C, (long long)C * C, x, 1, HW, (long long)C * HW, dx, HW, (long long)C * HW, 0, C, HW, C, B,
-                      1.f, nullptr, 0.f, nullptr, 0, 0, 0.f, nullptr, 0, stream_);
+                      1.f, nullptr, 0.f, nullptr, 0, 0, 0.f, nullptr, 2, stream_);
 }
 
 }  // extern "C"

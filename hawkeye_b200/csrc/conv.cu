@@ -20,13 +20,13 @@ namespace hk {
 // weight packing:  W [Cout][Cin][3][3]  ->  Wf [9][Cout][Cin]  and  Wd [9][Cin][Cout] (taps flipped)
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_weights_kernel(const float* __restrict__ W, float* __restrict__ Wf, float* __restrict__ Wd,
-                                    int Cout, int Cin) {
+                                    int Cout, int Cin, int round) {
   const size_t n = (size_t)Cout * Cin * 9;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int t = i % 9;
     const int ci = (i / 9) % Cin;
     const int co = i / ((size_t)9 * Cin);
-    const float v = tf32_round(W[i]);
+    const float v = round ? tf32_round(W[i]) : W[i];
     if (Wf) Wf[((size_t)t * Cout + co) * Cin + ci] = v;
     if (Wd) Wd[((size_t)(8 - t) * Cin + ci) * Cout + co] = v;
   }
@@ -54,6 +54,8 @@ struct ConvArgs {
   int tiles_w, tiles_h, tiles_n;
   int relu;
   int stride;          // 1 or 2 (N,H,W above are OUTPUT dims; the input map is H*stride x W*stride)
+  const float* addend; // [N,H,W,Cout] or null: raw partial sum added to the accumulator first (3xTF32 passes; may alias Y)
+  int no_round;        // 1: store fp32 as is (precise mode); 0: round to tf32 (the output feeds another MMA)
 };
 
 template <int BN>
@@ -151,6 +153,14 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tmem_ld_wait();
       const int co = co0 + c * 32;
       if (valid && co < a.Cout) {
+        if (a.addend) {
+          const float4* ad = reinterpret_cast<const float4*>(a.addend + pix * a.Cout + co);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = ad[j];
+            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+          }
+        }
         if (a.bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + co + j);
@@ -171,10 +181,15 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           }
         }
         float4* dst = reinterpret_cast<float4*>(a.Y + pix * a.Cout + co);
+        if (a.no_round) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(tf32_round(v[4 * j]), tf32_round(v[4 * j + 1]), tf32_round(v[4 * j + 2]),
-                               tf32_round(v[4 * j + 3]));
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(tf32_round(v[4 * j]), tf32_round(v[4 * j + 1]), tf32_round(v[4 * j + 2]),
+                                 tf32_round(v[4 * j + 3]));
+        }
       }
     }
   }
@@ -442,9 +457,31 @@ static int launch_conv_v2(const float* x, const float* wp, ConvArgs a, int N, in
   return 0;
 }
 
+static int conv3x3_igemm_1x(const float* x, const float* wp, const float* bias, const float* mask, const float* addend,
+                            float* y, int N, int H, int W, int Cin, int Cout, int relu, cudaStream_t stream, int stride,
+                            bool generic_only, int no_round);
+
 // x NHWC [N,H,W,Cin], wp packed [9][Cout][Cin] -> y NHWC [N,H,W,Cout]
 int conv3x3_igemm(const float* x, const float* wp, const float* bias, const float* mask, float* y, int N, int H, int W,
                   int Cin, int Cout, int relu, cudaStream_t stream, int stride = 1) {
+  if (!precise()) return conv3x3_igemm_1x(x, wp, bias, mask, nullptr, y, N, H, W, Cin, Cout, relu, stream, stride, false, 0);
+  // 3xTF32: y = epi(Xh*Wh + Xl*Wh + Xh*Wl), three passes of the same implicit-GEMM kernel chained through `addend`
+  HK_REQUIRE(x && wp && y, HK_ERR_ARG, "conv3x3: null pointer");
+  const size_t nx = (size_t)N * H * W * Cin, nw = (size_t)9 * Cout * Cin;
+  Scratch sx(2 * nx * sizeof(float), stream), sw(2 * nw * sizeof(float), stream);
+  HK_REQUIRE(sx.p && sw.p, HK_ERR_DRIVER, "conv3x3 (precise): cudaMallocAsync of the operand halves failed");
+  float *xh = sx.f(), *xl = xh + nx, *wh = sw.f(), *wl = wh + nw;
+  int r;
+  if ((r = tf32_split(x, xh, xl, nx, stream))) return r;
+  if ((r = tf32_split(wp, wh, wl, nw, stream))) return r;
+  if ((r = conv3x3_igemm_1x(xh, wl, nullptr, nullptr, nullptr, y, N, H, W, Cin, Cout, 0, stream, stride, true, 1))) return r;
+  if ((r = conv3x3_igemm_1x(xl, wh, nullptr, nullptr, y, y, N, H, W, Cin, Cout, 0, stream, stride, true, 1))) return r;
+  return conv3x3_igemm_1x(xh, wh, bias, mask, y, y, N, H, W, Cin, Cout, relu, stream, stride, true, 1);
+}
+
+static int conv3x3_igemm_1x(const float* x, const float* wp, const float* bias, const float* mask, const float* addend,
+                            float* y, int N, int H, int W, int Cin, int Cout, int relu, cudaStream_t stream, int stride,
+                            bool generic_only, int no_round) {
   // H, W are the INPUT dims; output is H/stride x W/stride (padding 1)
   const int Hin = H, Win = W;
   if (stride == 2) {
@@ -459,7 +496,8 @@ int conv3x3_igemm(const float* x, const float* wp, const float* bias, const floa
   ConvArgs a = {};
   a.Y = y; a.bias = bias; a.mask = mask; a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.relu = relu;
   a.stride = stride;
-  {
+  a.addend = addend; a.no_round = no_round;
+  if (!generic_only) {
     static int use_v2 = -1;
     if (use_v2 < 0) { const char* v = getenv("HK_CONV_V2"); use_v2 = v ? atoi(v) : 1; }
     if (use_v2 && stride == 1 && W % 16 == 0 && H % 8 == 0) {
@@ -667,8 +705,28 @@ static bool pick_wgrad_tile(int W, int H, int* TW, int* TH, int* TN) {
   return true;
 }
 
+static int conv3x3_wgrad_1x(const float* x, const float* dy, float* dwp, float* db, int N, int H, int W, int Cin, int Cout,
+                            cudaStream_t stream, bool zero_dw, bool zero_db);
+
 int conv3x3_wgrad(const float* x, const float* dy, float* dwp, float* db, int N, int H, int W, int Cin, int Cout,
                   cudaStream_t stream) {
+  if (!precise()) return conv3x3_wgrad_1x(x, dy, dwp, db, N, H, W, Cin, Cout, stream, true, true);
+  // 3xTF32: dW = dYh^T Xh + dYh^T Xl + dYl^T Xh accumulated by the kernel's own atomics; db = sum(dYh) + sum(dYl)
+  HK_REQUIRE(x && dy && dwp, HK_ERR_ARG, "conv3x3_wgrad: null pointer");
+  const size_t nx = (size_t)N * H * W * Cin, ny = (size_t)N * H * W * Cout;
+  Scratch sx(2 * nx * sizeof(float), stream), sy(2 * ny * sizeof(float), stream);
+  HK_REQUIRE(sx.p && sy.p, HK_ERR_DRIVER, "conv3x3_wgrad (precise): cudaMallocAsync of the operand halves failed");
+  float *xh = sx.f(), *xl = xh + nx, *yh = sy.f(), *yl = yh + ny;
+  int r;
+  if ((r = tf32_split(x, xh, xl, nx, stream))) return r;
+  if ((r = tf32_split(dy, yh, yl, ny, stream))) return r;
+  if ((r = conv3x3_wgrad_1x(xh, yh, dwp, db, N, H, W, Cin, Cout, stream, true, true))) return r;
+  if ((r = conv3x3_wgrad_1x(xl, yh, dwp, nullptr, N, H, W, Cin, Cout, stream, false, false))) return r;
+  return conv3x3_wgrad_1x(xh, yl, dwp, db, N, H, W, Cin, Cout, stream, false, false);
+}
+
+static int conv3x3_wgrad_1x(const float* x, const float* dy, float* dwp, float* db, int N, int H, int W, int Cin, int Cout,
+                            cudaStream_t stream, bool zero_dw, bool zero_db) {
   HK_REQUIRE(x && dy && dwp, HK_ERR_ARG, "conv3x3_wgrad: null pointer");
   HK_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0, HK_ERR_UNSUPPORTED, "conv3x3_wgrad: Cin=%d Cout=%d unsupported", Cin, Cout);
   WgradArgs a = {};
@@ -711,9 +769,12 @@ int conv3x3_wgrad(const float* x, const float* dy, float* dwp, float* db, int N,
   int r;
   if ((r = make_act_map(&tmDY, dy, N, H, W, Cout, a.TW, a.TH, a.TN, true))) return r;
   if ((r = make_act_map(&tmX, x, N, H, W, Cin, a.TW, a.TH + 2, a.TN, true))) return r;
-  cudaError_t e = cudaMemsetAsync(dwp, 0, (size_t)9 * Cout * Cin * sizeof(float), stream);
-  if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(dWp): %s", cudaGetErrorString(e));
-  if (db) {
+  cudaError_t e = cudaSuccess;
+  if (zero_dw) {
+    e = cudaMemsetAsync(dwp, 0, (size_t)9 * Cout * Cin * sizeof(float), stream);
+    if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(dWp): %s", cudaGetErrorString(e));
+  }
+  if (db && zero_db) {
     e = cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), stream);
     if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(db): %s", cudaGetErrorString(e));
   }
@@ -735,7 +796,7 @@ int conv3x3_wgrad(const float* x, const float* dy, float* dwp, float* db, int N,
 // first-layer weight gradient on the tensor cores: materialise the 3x3x3 patches as X27 [pix][32]
 // (27 taps, column 27 = 1.0 so that the GEMM's column 27 is the bias gradient, columns 28..31 = 0) and run
 // dW^T-partials[s] = dY[pix-range s]^T . X27[pix-range s]  as a batched (split-K) MN-major tcgen05 GEMM.
-__global__ void im2col_first_kernel(const float* __restrict__ x, float* __restrict__ x27, int N, int H, int W) {
+__global__ void im2col_first_kernel(const float* __restrict__ x, float* __restrict__ x27, int N, int H, int W, int round) {
   const long long total = (long long)N * H * W;
   for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
        pix += (long long)gridDim.x * blockDim.x) {
@@ -748,8 +809,8 @@ __global__ void im2col_first_kernel(const float* __restrict__ x, float* __restri
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
           const int hh = hq + kh - 1, ww = wq + kw - 1;
-          v[ci * 9 + kh * 3 + kw] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                                        ? tf32_round(__ldg(x + (((size_t)n * 3 + ci) * H + hh) * W + ww)) : 0.f;
+          float t = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(x + (((size_t)n * 3 + ci) * H + hh) * W + ww) : 0.f;
+          v[ci * 9 + kh * 3 + kw] = round ? tf32_round(t) : t;
         }
     v[27] = 1.f; v[28] = v[29] = v[30] = v[31] = 0.f;
     float4* dst = reinterpret_cast<float4*>(x27 + (size_t)pix * 32);
@@ -759,11 +820,12 @@ __global__ void im2col_first_kernel(const float* __restrict__ x, float* __restri
 }
 // w27[co][0..26] = tf32(w[co][ci][kh][kw]), w27[co][27] = bias[co] (x27 column 27 is 1.0), rest 0
 __global__ void pack_first_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias,
-                                          float* __restrict__ w27, int Cout) {
+                                          float* __restrict__ w27, int Cout, int round) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Cout * 32) return;
   const int co = i / 32, r = i % 32;
-  w27[i] = r < 27 ? tf32_round(w[co * 27 + r]) : (r == 27 && bias ? tf32_round(bias[co]) : 0.f);
+  const float t = r < 27 ? w[co * 27 + r] : (r == 27 && bias ? bias[co] : 0.f);
+  w27[i] = round ? tf32_round(t) : t;
 }
 // dw[co][r] = sum_s part[s][co][r] (r<27), db[co] = sum_s part[s][co][27]
 __global__ void first_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw,
@@ -875,7 +937,8 @@ extern "C" {
 
 int hk_conv3x3_pack_weights(const float* w, float* w_fwd, float* w_dgrad, int Cout, int Cin, void* stream) {
   HK_REQUIRE(w && (w_fwd || w_dgrad), HK_ERR_ARG, "hk_conv3x3_pack_weights: null pointer");
-  pack_weights_kernel<<<grid_for((size_t)Cout * Cin * 9, 256), 256, 0, (cudaStream_t)stream>>>(w, w_fwd, w_dgrad, Cout, Cin);
+  pack_weights_kernel<<<grid_for((size_t)Cout * Cin * 9, 256), 256, 0, (cudaStream_t)stream>>>(w, w_fwd, w_dgrad, Cout, Cin,
+                                                                                             precise() ? 0 : 1);
   HK_LAUNCH_CHECK("pack_weights_kernel");
   return 0;
 }
@@ -929,9 +992,10 @@ int hk_conv3x3_first_fwd(const float* x_nchw, const float* w, const float* bias,
   HK_REQUIRE(P < (1ll << 31), HK_ERR_UNSUPPORTED, "hk_conv3x3_first_fwd: too many pixels");
   float* x27 = static_cast<float*>(workspace);
   float* w27 = x27 + (size_t)P * 32;
-  im2col_first_kernel<<<grid_for((size_t)P, 128), 128, 0, stream>>>(x_nchw, x27, N, H, W);
+  const int round = precise() ? 0 : 1;
+  im2col_first_kernel<<<grid_for((size_t)P, 128), 128, 0, stream>>>(x_nchw, x27, N, H, W, round);
   HK_LAUNCH_CHECK("im2col_first_kernel");
-  pack_first_weights_kernel<<<(Cout * 32 + 127) / 128, 128, 0, stream>>>(w, bias, w27, Cout);
+  pack_first_weights_kernel<<<(Cout * 32 + 127) / 128, 128, 0, stream>>>(w, bias, w27, Cout, round);
   HK_LAUNCH_CHECK("pack_first_weights_kernel");
   return hk_gemm_tf32(x27, 0, 32, 0, w27, 0, 32, 0, y_nhwc, Cout, 0, 0, (int)P, Cout, 32, 1, 1.f, nullptr, 0.f, nullptr,
                       0, 0, 0.f, nullptr, 3 /*relu + tf32 round*/, stream_);

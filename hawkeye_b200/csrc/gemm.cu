@@ -150,7 +150,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float* Cb = epi.C + (long long)bz * epi.strideC;
       const float* Db = epi.D ? epi.D + (long long)bz * epi.strideD : nullptr;
       const float* Dlb = (epi.D && epi.D_lo) ? epi.D_lo + (long long)bz * epi.strideD : nullptr;
-      const float* Eb = epi.E ? epi.E + (long long)bz * epi.strideC : nullptr;
+      const long long ldE = epi.ldE ? epi.ldE : epi.ldc;
+      const float* Eb = epi.E ? epi.E + (long long)bz * (epi.ldE ? epi.strideE : epi.strideC) : nullptr;
       float* Clb = epi.C_lo ? epi.C_lo + (long long)bz * epi.strideC : nullptr;
       const bool simple = !Eb && !Db && !Clb && epi.diag == 0.f && !epi.trans_c;
 #pragma unroll 1
@@ -182,7 +183,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 32; ++j) {
             const int col = col0 + j;
             float acc = v[j];
-            if (Eb && col < N) acc += Eb[(long long)row * epi.ldc + col];
+            if (Eb && col < N) acc += Eb[(long long)row * ldE + col];
             float o = alpha * acc;
             if (col == row) o += epi.diag;
             if (Db && col < N) {
@@ -286,8 +287,68 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   return 0;
 }
 
+__global__ void tf32_split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float h = tf32_round(v);
+    if (hi) hi[i] = h;
+    if (lo) lo[i] = tf32_round(v - h);
+  }
+}
+
+int tf32_split(const float* x, float* hi, float* lo, size_t n, cudaStream_t stream) {
+  if (!n) return 0;
+  size_t g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  tf32_split_kernel<<<(unsigned)g, 256, 0, stream>>>(x, hi, lo, n);
+  HK_LAUNCH_CHECK("tf32_split_kernel");
+  return 0;
+}
+
+// floats spanned by a strided operand: `batch` matrices of `rows` x `cols` (cols contiguous), leading dimension ld
+static size_t operand_extent(long long rows, long long cols, long long ld, long long stride, int batch) {
+  return (size_t)((long long)(batch - 1) * (stride > 0 ? stride : 0) + (rows - 1) * ld + cols);
+}
+
+// 3xTF32: A.B ~= Ah.Bh + Al.Bh + Ah.Bl with (hi, lo) = tf32 halves of the operands, chained through the epilogue's raw
+// addend E so the caller's epilogue (alpha, diag, D, ReLU, transposed store ...) is applied once, to the full sum.
+static int gemm_tf32_3x(const float* A, int a_mn, long long lda, long long strideA, const float* B, int b_mn, long long ldb,
+                        long long strideB, const GemmEpi& epi, int M, int N, int K, int batch, cudaStream_t st) {
+  const size_t nA = operand_extent(a_mn ? K : M, a_mn ? M : K, lda, strideA, batch);
+  const bool same = (A == B && a_mn == b_mn && lda == ldb && strideA == strideB && M == N);
+  const size_t nB = same ? 0 : operand_extent(b_mn ? K : N, b_mn ? N : K, ldb, strideB, batch);
+  Scratch sa(2 * nA * sizeof(float), st), sb(2 * (nB ? nB : 4) * sizeof(float), st);
+  Scratch tmp((size_t)batch * M * N * sizeof(float), st);
+  HK_REQUIRE(sa.p && sb.p && tmp.p, HK_ERR_DRIVER, "gemm (precise): cudaMallocAsync of the operand halves failed");
+  float *Ah = sa.f(), *Al = Ah + nA;
+  float *Bh = same ? Ah : sb.f(), *Bl = same ? Al : Bh + nB;
+  int r;
+  if ((r = tf32_split(A, Ah, Al, nA, st))) return r;
+  if (!same && (r = tf32_split(B, Bh, Bl, nB, st))) return r;
+  GemmEpi e = {};
+  e.C = tmp.f(); e.ldc = N; e.strideC = (long long)M * N; e.alpha = 1.f;
+  e.E = epi.E; e.ldE = epi.E ? (epi.ldE ? epi.ldE : epi.ldc) : 0; e.strideE = epi.E ? (epi.ldE ? epi.strideE : epi.strideC) : 0;
+  if ((r = gemm_tf32_1x(Ah, a_mn, lda, strideA, Bl, b_mn, ldb, strideB, e, M, N, K, batch, st))) return r;   // tmp = Ah.Bl (+E)
+  e.E = tmp.f(); e.ldE = N; e.strideE = (long long)M * N;
+  if ((r = gemm_tf32_1x(Al, a_mn, lda, strideA, Bh, b_mn, ldb, strideB, e, M, N, K, batch, st))) return r;   // tmp += Al.Bh
+  GemmEpi f = epi;
+  f.E = tmp.f(); f.ldE = N; f.strideE = (long long)M * N;
+  f.relu &= ~2;                                                                                             // no rounding
+  return gemm_tf32_1x(Ah, a_mn, lda, strideA, Bh, b_mn, ldb, strideB, f, M, N, K, batch, st);
+}
+
 int gemm_tf32(const float* A, int a_mn, long long lda, long long strideA, const float* B, int b_mn, long long ldb,
               long long strideB, const GemmEpi& epi, int M, int N, int K, int batch, cudaStream_t stream) {
+  if (precise()) {
+    HK_REQUIRE(A && B && epi.C, HK_ERR_ARG, "gemm: null pointer");
+    HK_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, HK_ERR_ARG, "gemm: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
+    return gemm_tf32_3x(A, a_mn, lda, strideA, B, b_mn, ldb, strideB, epi, M, N, K, batch, stream);
+  }
+  return gemm_tf32_1x(A, a_mn, lda, strideA, B, b_mn, ldb, strideB, epi, M, N, K, batch, stream);
+}
+
+int gemm_tf32_1x(const float* A, int a_mn, long long lda, long long strideA, const float* B, int b_mn, long long ldb,
+                 long long strideB, const GemmEpi& epi, int M, int N, int K, int batch, cudaStream_t stream) {
   HK_REQUIRE(A && B && epi.C, HK_ERR_ARG, "gemm: null pointer");
   HK_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, HK_ERR_ARG, "gemm: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
   HK_REQUIRE(batch <= 65535, HK_ERR_UNSUPPORTED, "gemm: batch %d > 65535", batch);
@@ -314,7 +375,7 @@ extern "C" int hk_gemm_tf32(const float* A, int a_mn_major, long long lda, long 
   epi.alpha_vec = alpha_vec; epi.beta_vec = beta_vec;
   epi.alpha = alpha; epi.beta = beta; epi.diag = diag;
   epi.trans_c = trans_c; epi.relu = relu;
-  epi.C_lo = nullptr; epi.D_lo = nullptr; epi.E = nullptr;
+  epi.C_lo = nullptr; epi.D_lo = nullptr; epi.E = nullptr; epi.ldE = 0; epi.strideE = 0;
   return hk::gemm_tf32(A, a_mn_major, lda, strideA, B, b_mn_major, ldb, strideB, epi, M, N, K, batch,
                        static_cast<cudaStream_t>(stream));
 }

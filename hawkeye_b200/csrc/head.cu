@@ -22,7 +22,7 @@ __global__ void splitk_reduce_bias_kernel(const float* __restrict__ partial, con
 // dlogits = (softmax - ((1-eps) onehot + eps/K)) * grad_scale / B
 __global__ void softmax_ce_ls_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
                                      float* __restrict__ loss, float* __restrict__ dlogits, int* __restrict__ correct,
-                                     int B, int K, float eps, float grad_scale) {
+                                     int B, int K, float eps, float grad_scale, int round) {
   __shared__ float s_loss[32];
   __shared__ int s_corr[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -61,7 +61,8 @@ __global__ void softmax_ce_ls_kernel(const float* __restrict__ logits, const lon
       for (int k = lane; k < K; k += 32) {
         const float p = expf(row[k] - lse);
         const float t = (k == y ? (1.f - eps) : 0.f) + eps / (float)K;
-        dlogits[(size_t)b * K + k] = (p - t) * sc;
+        const float g = (p - t) * sc;
+        dlogits[(size_t)b * K + k] = round ? tf32_round(g) : g;     // operand of the classifier dgrad / wgrad MMAs
       }
     }
   }
@@ -189,7 +190,7 @@ int hk_softmax_ce_ls(const float* logits, const long long* labels, float* loss, 
                      int K, float label_smoothing, float grad_scale, void* stream) {
   HK_REQUIRE(logits && labels && loss, HK_ERR_ARG, "hk_softmax_ce_ls: null pointer");
   softmax_ce_ls_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, labels, loss, dlogits, correct, B, K,
-                                                           label_smoothing, grad_scale);
+                                                           label_smoothing, grad_scale, precise() ? 0 : 1);
   HK_LAUNCH_CHECK("softmax_ce_ls_kernel");
   return 0;
 }

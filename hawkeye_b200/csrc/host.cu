@@ -2,6 +2,7 @@
 #include "host.h"
 
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/hawkeye_b200.h"
@@ -9,6 +10,24 @@
 namespace hk {
 
 std::atomic<long long> g_launches{0};
+static std::atomic<int> g_precise{-1};   // -1: not yet read from $HK_PRECISE
+
+bool precise() {
+  int v = g_precise.load();
+  if (v < 0) {
+    const char* e = getenv("HK_PRECISE");
+    v = (e && atoi(e) != 0) ? 1 : 0;
+    g_precise.store(v);
+  }
+  return v != 0;
+}
+
+Scratch::Scratch(size_t bytes, cudaStream_t stream) : s(stream) {
+  if (cudaMallocAsync(&p, bytes ? bytes : 16, s) != cudaSuccess) { p = nullptr; (void)cudaGetLastError(); }
+}
+Scratch::~Scratch() {
+  if (p) cudaFreeAsync(p, s);
+}
 
 char* last_error_buf() {
   static thread_local char buf[512] = {0};
@@ -95,6 +114,8 @@ extern "C" {
 
 const char* hk_version(void) { return "hawkeye_b200 0.1 (sm_100a; tcgen05/TMA)"; }
 const char* hk_last_error(void) { return hk::last_error_buf(); }
+void hk_set_precise(int on) { hk::g_precise.store(on ? 1 : 0); }
+int hk_get_precise(void) { return hk::precise() ? 1 : 0; }
 long long hk_launch_count(void) { return hk::g_launches.load(); }
 void hk_reset_launch_count(void) { hk::g_launches.store(0); }
 

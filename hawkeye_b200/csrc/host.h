@@ -33,6 +33,25 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int make_tmap(CUtensorMap* out, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, bool mn_major = false, const uint32_t* elem_strides = nullptr);
 
+// ---- precise mode (parity runs; hk_set_precise / $HK_PRECISE) -------------------------------------------------------
+// 0 (default): every tensor-core product is single-pass TF32 and producers round what they hand to the next MMA.
+// 1          : 3xTF32 — every MMA operand is split into (hi, lo) tf32 halves and A.B ~= Ah.Bh + Al.Bh + Ah.Bl is accumulated
+//              by the SAME kernels (three passes chained through their epilogue addend); nothing is rounded on store.
+//              fp32-class accuracy at >3x the cost: a test mode, which is why it may allocate stream-ordered scratch.
+bool precise();
+// stream-ordered scratch buffer (cudaMallocAsync / cudaFreeAsync on `s`); used by the precise mode only
+struct Scratch {
+  void* p = nullptr;
+  cudaStream_t s;
+  Scratch(size_t bytes, cudaStream_t stream);
+  ~Scratch();
+  float* f() const { return static_cast<float*>(p); }
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+};
+// hi = rn_tf32(x), lo = rn_tf32(x - hi)  (elementwise over n floats; hi or lo may be null)
+int tf32_split(const float* x, float* hi, float* lo, size_t n, cudaStream_t stream);
+
 #define HK_REQUIRE(cond, code, ...) \
   do {                              \
     if (!(cond)) return hk::set_error(code, __VA_ARGS__); \

@@ -27,26 +27,26 @@ static int mm3(Pair A, Pair B, Pair C, float* tmp, int n, int batch, float alpha
   const long long s = (long long)n * n;
   GemmEpi e = {};
   e.C = tmp; e.ldc = n; e.strideC = s; e.alpha = 1.f;
-  int r = gemm_tf32(A.hi, 0, n, s, B.lo, 1, n, s, e, n, n, n, batch, st);           // tmp  = Ah.Bl
+  int r = gemm_tf32_1x(A.hi, 0, n, s, B.lo, 1, n, s, e, n, n, n, batch, st);           // tmp  = Ah.Bl
   if (r) return r;
   e.E = tmp;
-  if ((r = gemm_tf32(A.lo, 0, n, s, B.hi, 1, n, s, e, n, n, n, batch, st))) return r;  // tmp += Al.Bh  (E aliases C: each
+  if ((r = gemm_tf32_1x(A.lo, 0, n, s, B.hi, 1, n, s, e, n, n, n, batch, st))) return r;  // tmp += Al.Bh  (E aliases C: each
   GemmEpi f = {};                                                                     //  element read then written by one thread)
   f.C = C.hi; f.C_lo = C.lo; f.ldc = n; f.strideC = s; f.E = tmp;
   f.alpha = alpha; f.alpha_vec = alpha_vec; f.diag = diag;
   if (D) { f.D = D->hi; f.D_lo = D->lo; f.ldd = n; f.strideD = s; f.beta = beta; }
-  return gemm_tf32(A.hi, 0, n, s, B.hi, 1, n, s, f, n, n, n, batch, st);            // C = alpha*(Ah.Bh + tmp) + ...
+  return gemm_tf32_1x(A.hi, 0, n, s, B.hi, 1, n, s, f, n, n, n, batch, st);            // C = alpha*(Ah.Bh + tmp) + ...
 }
 
 // ------------------------------------------------------------------------------------------------ small kernels
 // centre the rows of X [B*C][M] (subtract the spatial mean) and round to tf32:  X I_hat X^T = Xc Xc^T / M
-__global__ void center_rows_kernel(const float* __restrict__ x, float* __restrict__ xc, int M) {
+__global__ void center_rows_kernel(const float* __restrict__ x, float* __restrict__ xc, int M, int round) {
   const size_t row = blockIdx.x;
   const float* p = x + row * M;
   float s = 0.f;
   for (int i = threadIdx.x; i < M; i += 32) s += p[i];
   s = warp_sum(s) / (float)M;
-  for (int i = threadIdx.x; i < M; i += 32) xc[row * M + i] = tf32_round(p[i] - s);
+  for (int i = threadIdx.x; i < M; i += 32) xc[row * M + i] = round ? tf32_round(p[i] - s) : p[i] - s;
 }
 
 // normA[b] = trace(x[b]); A = x / normA as a (hi, lo) pair
@@ -164,7 +164,7 @@ int hk_covpool_fwd(const float* x, float* cov, float* xc, int B, int C, int M, v
   cudaStream_t st = (cudaStream_t)stream_;
   HK_REQUIRE(x && cov && xc, HK_ERR_ARG, "hk_covpool_fwd: null pointer");
   HK_REQUIRE(M % 4 == 0, HK_ERR_UNSUPPORTED, "hk_covpool_fwd: H*W=%d must be a multiple of 4", M);
-  center_rows_kernel<<<(unsigned)((size_t)B * C), 32, 0, st>>>(x, xc, M);
+  center_rows_kernel<<<(unsigned)((size_t)B * C), 32, 0, st>>>(x, xc, M, precise() ? 0 : 1);
   HK_LAUNCH_CHECK("center_rows_kernel");
   GemmEpi e = {};
   e.C = cov; e.ldc = C; e.strideC = (long long)C * C; e.alpha = 1.f / (float)M;

@@ -18,7 +18,7 @@ static inline int rgrid(size_t n, int block) {
 // ------------------------------------------------------------------------------------------------ stem (resnet.py:176)
 // X147[pix][ci*49 + kh*7 + kw] = x[n][ci][2*ho+kh-3][2*wo+kw-3] (0 outside), columns 147..159 = 0; tf32-rounded
 __global__ void stem_im2col_kernel(const float* __restrict__ x, float* __restrict__ o, int N, int H, int W, int Ho,
-                                   int Wo) {
+                                   int Wo, int round) {
   const long long total = (long long)N * Ho * Wo * 40;   // 40 float4 per pixel
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int q = (int)(i % 40);
@@ -32,18 +32,21 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, float* __restric
       if (col < 147) {
         const int ci = col / 49, r = col % 49, kh = r / 7, kw = r % 7;
         const int hh = 2 * ho + kh - 3, ww = 2 * wo + kw - 3;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) t = tf32_round(__ldg(x + (((size_t)n * 3 + ci) * H + hh) * W + ww));
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+          t = __ldg(x + (((size_t)n * 3 + ci) * H + hh) * W + ww);
+          if (round) t = tf32_round(t);
+        }
       }
       v[e] = t;
     }
     reinterpret_cast<float4*>(o)[i] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
-__global__ void pack_stem_weights_kernel(const float* __restrict__ w, float* __restrict__ o, int Cout) {
+__global__ void pack_stem_weights_kernel(const float* __restrict__ w, float* __restrict__ o, int Cout, int round) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Cout * 160) return;
   const int co = i / 160, c = i % 160;
-  o[i] = c < 147 ? tf32_round(w[co * 147 + c]) : 0.f;
+  o[i] = c < 147 ? (round ? tf32_round(w[co * 147 + c]) : w[co * 147 + c]) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------ BatchNorm2d (train)
@@ -103,7 +106,7 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ part, int nbl
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ res, float* __restrict__ y,
-                                size_t total4, int C4, int relu) {
+                                size_t total4, int C4, int relu, int round) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
     const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -117,7 +120,8 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    reinterpret_cast<float4*>(y)[i] = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
+    if (round) o = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
+    reinterpret_cast<float4*>(y)[i] = o;
   }
 }
 // backward reductions: part[blk][0][c] = sum dy', part[blk][1][c] = sum dy' * xhat,  dy' = dy * (y > 0 if relu)
@@ -178,7 +182,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __
                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
                                     const float* __restrict__ dgamma, const float* __restrict__ dbeta,
                                     float* __restrict__ dx, float* __restrict__ dres, size_t total4, int C4, float invP,
-                                    int relu) {
+                                    int relu, int round) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
     float4 g = reinterpret_cast<const float4*>(dy)[i];
@@ -196,7 +200,8 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __
     o.y = ga.y * is.y * (g.y - db.y * invP - (v.y - m.y) * is.y * dg.y * invP);
     o.z = ga.z * is.z * (g.z - db.z * invP - (v.z - m.z) * is.z * dg.z * invP);
     o.w = ga.w * is.w * (g.w - db.w * invP - (v.w - m.w) * is.w * dg.w * invP);
-    reinterpret_cast<float4*>(dx)[i] = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
+    if (round) o = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
+    reinterpret_cast<float4*>(dx)[i] = o;
   }
 }
 
@@ -350,13 +355,13 @@ extern "C" {
 int hk_stem_im2col(const float* x_nchw, float* x147, int N, int H, int W, void* stream) {
   HK_REQUIRE(x_nchw && x147, HK_ERR_ARG, "hk_stem_im2col: null pointer");
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
-  stem_im2col_kernel<<<rgrid((size_t)N * Ho * Wo * 40, 256), 256, 0, (cudaStream_t)stream>>>(x_nchw, x147, N, H, W, Ho, Wo);
+  stem_im2col_kernel<<<rgrid((size_t)N * Ho * Wo * 40, 256), 256, 0, (cudaStream_t)stream>>>(x_nchw, x147, N, H, W, Ho, Wo, precise() ? 0 : 1);
   HK_LAUNCH_CHECK("stem_im2col_kernel");
   return 0;
 }
 int hk_pack_stem_weights(const float* w, float* w147, int Cout, void* stream) {
   HK_REQUIRE(w && w147, HK_ERR_ARG, "hk_pack_stem_weights: null pointer");
-  pack_stem_weights_kernel<<<(Cout * 160 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, w147, Cout);
+  pack_stem_weights_kernel<<<(Cout * 160 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, w147, Cout, precise() ? 0 : 1);
   HK_LAUNCH_CHECK("pack_stem_weights_kernel");
   return 0;
 }
@@ -379,7 +384,7 @@ int hk_bn_fwd(const float* x, const float* gamma, const float* beta, const float
                                                          running_mean, running_var);
   HK_LAUNCH_CHECK("bn_stats_finalize_kernel");
   bn_apply_kernel<<<rgrid((size_t)P * C4, 256), 256, 0, st>>>(x, save_mean, save_invstd, gamma, beta, residual, y,
-                                                            (size_t)P * C4, C4, relu);
+                                                            (size_t)P * C4, C4, relu, precise() ? 0 : 1);
   HK_LAUNCH_CHECK("bn_apply_kernel");
   return 0;
 }
@@ -389,7 +394,7 @@ int hk_bn_apply(const float* x, const float* mean, const float* invstd, const fl
                 const float* residual, float* y, long long P, int C, int relu, void* stream_) {
   HK_REQUIRE(x && mean && invstd && gamma && beta && y && C % 4 == 0, HK_ERR_ARG, "hk_bn_apply: bad args");
   bn_apply_kernel<<<rgrid((size_t)P * (C / 4), 256), 256, 0, (cudaStream_t)stream_>>>(x, mean, invstd, gamma, beta, residual, y,
-                                                                                   (size_t)P * (C / 4), C / 4, relu);
+                                                                                   (size_t)P * (C / 4), C / 4, relu, precise() ? 0 : 1);
   HK_LAUNCH_CHECK("bn_apply_kernel");
   return 0;
 }
@@ -410,7 +415,7 @@ int hk_bn_bwd(const float* x, const float* y, const float* dy, const float* gamm
   bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, st>>>(part, nb, C, dgamma, dbeta);
   HK_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   bn_bwd_apply_kernel<<<rgrid((size_t)P * C4, 256), 256, 0, st>>>(x, y, dy, save_mean, save_invstd, gamma, dgamma, dbeta, dx,
-                                                                dres, (size_t)P * C4, C4, 1.f / (float)P, relu);
+                                                                dres, (size_t)P * C4, C4, 1.f / (float)P, relu, precise() ? 0 : 1);
   HK_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return 0;
 }

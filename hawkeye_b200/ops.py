@@ -10,6 +10,12 @@ from . import _lib
 
 VGG16_D = (64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M')
 
+# Parity tests only: when set to a list, forward passes append the decisions they took at the non-smooth points of the
+# path, in execution order — ('relu', y NHWC) after every ReLU, ('pool2', x NHWC) before every 2x2 max-pool,
+# ('pool3', argmax u8 NHWC, input shape) for the ResNet stem pool, ('ssqrt', bins) for CBCNN's signed square root —
+# so that a CPU oracle can be evaluated on the same branch of the piecewise-smooth function (oracle.hop_oracle.MaskTape).
+CAPTURE = None
+
 
 def _check_cuda(*ts):
     for t in ts:
@@ -182,6 +188,8 @@ class VGGFeaturesFn(Function):
                     rec = dict(kind='conv', inp=cur, out=y, wd=wd, H=H, W=W, cin=C, cout=cout,
                                inp_is_relu=(records[-1]['kind'] != 'pool'))
                 records.append(rec)
+                if CAPTURE is not None:
+                    CAPTURE.append(('relu', y))
                 cur, C = y, cout
                 li += 1
             else:
@@ -189,6 +197,8 @@ class VGGFeaturesFn(Function):
                 Ho, Wo = H // 2, W // 2
                 out = torch.empty((N, C, Ho, Wo) if last else (N, Ho, Wo, C), device=dev, dtype=torch.float32)
                 _lib.call('hk_maxpool2x2_fwd', cur, out, N, H, W, C, 1 if last else 0, s)
+                if CAPTURE is not None:
+                    CAPTURE.append(('pool2', cur))
                 records.append(dict(kind='pool', inp=cur, H=H, W=W, C=C, last=last))
                 cur, H, W = out, Ho, Wo
         if save:
@@ -296,6 +306,8 @@ class CompactBilinearPoolFn(Function):
         y = torch.empty(B, d, device=x.device, dtype=torch.float32)
         pre = torch.empty(B, d, device=x.device, dtype=torch.float32)
         _lib.call('hk_cbp_fwd', x, h1, h2, s1, s2, y, pre, B, C, H * W, d, _lib.stream_ptr())
+        if CAPTURE is not None:
+            CAPTURE.append(('ssqrt', pre))
         ctx.save_for_backward(x, pre, h1, h2, s1, s2)
         ctx.d = d
         return y

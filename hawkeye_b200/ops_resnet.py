@@ -6,7 +6,7 @@ conv unit = convolution (tcgen05 GEMM / implicit GEMM) -> train-mode BatchNorm (
 import torch
 from torch.autograd import Function
 
-from . import _lib
+from . import _lib, ops as _ops
 from .ops import _check_cuda, _f32c, _ws
 
 BN_EPS = 1e-5
@@ -84,6 +84,8 @@ class Unit:
             mean = bn.running_mean
             invstd = torch.rsqrt(bn.running_var + bn.eps)
             _lib.call('hk_bn_apply', c, mean, invstd, gamma, beta, residual, y, P, cout, int(self.relu), s)
+        if _ops.CAPTURE is not None and self.relu:
+            _ops.CAPTURE.append(('relu', y))
         if save:
             rec.update(c=c, y=y if self.relu else None, mean=mean, invstd=invstd, P=P, cout=cout, w=w, gamma=gamma,
                        shape=(N, Ho, Wo), has_res=residual is not None)
@@ -190,6 +192,8 @@ class ResNetTrunkFn(Function):
         p = torch.empty(N, Hp, Wp, C, device=x.device, dtype=torch.float32)
         am = torch.empty(N, Hp, Wp, C, device=x.device, dtype=torch.uint8) if save else None
         _lib.call('hk_maxpool3x3s2_fwd', y, p, am, N, H, W, C, s)
+        if _ops.CAPTURE is not None:
+            _ops.CAPTURE.append(('pool3', am, (N, H, W, C)))
         recs.append(('stem', r, (tuple(y.shape), am) if save else None))
         cur = p
         for (u1, u2, u3, ds) in plan.blocks:

@@ -27,6 +27,18 @@ const char* hk_last_error(void);
 long long hk_launch_count(void);      /* kernels launched by this library on the calling thread */
 void hk_reset_launch_count(void);
 
+/* ---- precision mode (process-wide; default 0, or $HK_PRECISE at first use) ---------------------------------------
+ * 0: single-pass TF32 tensor-core products (tcgen05 kind::tf32 keeps 10 mantissa bits of each operand); every kernel
+ *    that produces an operand of a later MMA rounds it to tf32 on store (round-to-nearest), so outputs of
+ *    hk_conv3x3_*, hk_bn_*, hk_bilinear_pool_fwd, hk_cbp_fwd carry a 2^-11 relative quantisation.  Meets the 1e-3
+ *    forward tolerance of the path; gradients below ReLU / max-pool kinks then differ from an fp32 run by branch
+ *    flips (see tests/matched.py).
+ * 1: 3xTF32 — every MMA operand is split into (hi, lo) tf32 halves and  A.B ~= Ah.Bh + Al.Bh + Ah.Bl  is accumulated
+ *    by the same kernels in three passes; nothing is rounded on store.  fp32-class results (for parity runs against
+ *    the fp32 reference) at more than 3x the cost; this mode allocates stream-ordered scratch (cudaMallocAsync). */
+void hk_set_precise(int on);
+int hk_get_precise(void);
+
 /* ---- generic batched TF32 tensor-core GEMM (tcgen05 + TMA) -------------------------------------
  * C[b] = alpha*alpha_vec[b] * A[b].B[b] + diag*I + beta*beta_vec[b] * D[b]   (ReLU optional; C optionally transposed)
  * A logical [M,K]: a_mn_major=0 -> A[m*lda+k]; 1 -> A[k*lda+m].   B logical [K,N]: b_mn_major=0 -> B[n*ldb+k]; 1 -> B[k*ldb+n].
@@ -45,7 +57,9 @@ size_t hk_bilinear_pool_fwd_workspace_bytes(int B, int C, int HW);
 void hk_debug_gram_trace(void* buf);
 int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, int C, int HW, void* workspace,
                          size_t workspace_bytes, void* stream);
-/* backward of the same (what autograd derives for BCNN.py:13-27): dx [B,C,HW] from dy [B,C*C]; z is recomputed. */
+/* backward of the same (what autograd derives for BCNN.py:13-27): dx [B,C,HW] from dy [B,C*C]; z is recomputed.
+ * Default precision mode: y (forward) and dx (backward) are rounded to tf32 on store — they are operands of the next
+ * MMA (classifier / last conv dgrad) — and the forward uses sqrt.approx (2^-22 rel.); hk_set_precise(1): fp32 as computed. */
 size_t hk_bilinear_pool_bwd_workspace_bytes(int B, int C, int HW);
 int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int C, int HW, void* workspace,
                          size_t workspace_bytes, void* stream);
@@ -150,7 +164,9 @@ int hk_linear_dgrad(const float* dy, const float* w, float* dx, int B, int F, in
 int hk_linear_wgrad(const float* dy, const float* x, float* dw, float* db, int B, int F, int N, void* stream);
 
 /* ---- nn.CrossEntropyLoss(label_smoothing) fwd+bwd (train.py:211-212, :315-319); labels int64 ----------------
- * loss[0] = mean loss; dlogits (optional) = dloss/dlogits * grad_scale; correct (optional) = #argmax==label. */
+ * loss[0] = mean loss; dlogits (optional) = dloss/dlogits * grad_scale; correct (optional) = #argmax==label.
+ * In the default precision mode dlogits is rounded to tf32 on store (it is the operand of the classifier's dgrad / wgrad
+ * MMAs, which would otherwise truncate it); hk_set_precise(1) stores it unrounded. */
 int hk_softmax_ce_ls(const float* logits, const long long* labels, float* loss, float* dlogits, int* correct, int B,
                      int K, float label_smoothing, float grad_scale, void* stream);
 

@@ -18,6 +18,73 @@ import torch
 import torch.nn.functional as F
 
 # --------------------------------------------------------------------------------------
+# Non-smooth points of the path (ReLU, max-pool arg-max, CBCNN's signed sqrt).  `Plain` is what the reference does.
+# `MaskTape` replays decisions recorded from ANOTHER forward pass of the same network (the GPU's): ReLU becomes a
+# multiplication by the recorded 0/1 mask, max-pool a gather at the recorded arg-max, the signed square root takes its
+# derivative at the recorded bin values.  The function is then identical to the reference's wherever both forwards made
+# the same decisions, and smooth in between — so its gradients are what the other implementation must reproduce up to
+# its arithmetic error alone ("matched-activation" parity, tests/test_gpu_matched.py).
+# --------------------------------------------------------------------------------------
+
+
+class Plain:
+    @staticmethod
+    def relu(x):
+        return F.relu(x)
+
+    @staticmethod
+    def maxpool(x, k, s, p=0):
+        return F.max_pool2d(x, k, s, p)
+
+    @staticmethod
+    def signed_sqrt(v):
+        return torch.sign(v) * torch.sqrt(torch.abs(v) + 1e-10)                 # CBCNN.py:132
+
+
+class _SignedSqrtAt(torch.autograd.Function):
+    """forward: sign(v) sqrt(|v|+1e-10) of v itself; backward: the derivative evaluated at the recorded values."""
+
+    @staticmethod
+    def forward(ctx, v, rec):
+        ctx.save_for_backward(rec)
+        return torch.sign(v) * torch.sqrt(torch.abs(v) + 1e-10)
+
+    @staticmethod
+    def backward(ctx, g):
+        (rec,) = ctx.saved_tensors
+        return g * (rec != 0).to(g.dtype) / (2 * torch.sqrt(torch.abs(rec) + 1e-10)), None
+
+
+class MaskTape:
+    """items, in execution order: ('relu', bool mask NCHW) | ('pool', int64 flat H*W indices [N,C,Ho,Wo]) |
+    ('ssqrt', recorded pre-sqrt values [B,d])."""
+
+    def __init__(self, items):
+        self.items, self.i = list(items), 0
+
+    def _next(self, kind):
+        k, v = self.items[self.i]
+        assert k == kind, f'tape out of step: wanted {kind}, recorded {k} at {self.i}'
+        self.i += 1
+        return v
+
+    def relu(self, x):
+        m = self._next('relu')
+        assert m.shape == x.shape, (m.shape, x.shape)
+        return x * m.to(x.dtype)
+
+    def maxpool(self, x, k, s, p=0):
+        idx = self._next('pool')
+        return x.flatten(2).gather(2, idx.flatten(2)).view(idx.shape)
+
+    def signed_sqrt(self, v):
+        return _SignedSqrtAt.apply(v, self._next('ssqrt').to(v.dtype))
+
+    def done(self):
+        return self.i == len(self.items)
+
+
+# --------------------------------------------------------------------------------------
 # BCNN bilinear pooling  (model/methods/BCNN.py:13-27)
 # --------------------------------------------------------------------------------------
 
@@ -80,7 +147,7 @@ def sketch_matrix(h, s, output_dim, dtype=torch.float32):
     return m
 
 
-def cbp_fwd(x, output_dim, hashes=None):
+def cbp_fwd(x, output_dim, hashes=None, nl=Plain):
     """x: [B,C,H,W] -> [B,d].  The reference's FFT route (CBCNN.py:96-135)."""
     B, C, H, W = x.shape
     h1, s1, h2, s2 = hashes if hashes is not None else cbp_hashes(C, output_dim)
@@ -91,7 +158,7 @@ def cbp_fwd(x, output_dim, hashes=None):
     prod = torch.fft.fft(sk1) * torch.fft.fft(sk2)                  # :120-123
     cbp = torch.fft.ifft(prod).real.view(B, H, W, output_dim)       # :125-127
     cbp = cbp.sum(dim=1).sum(dim=1)                                 # :130
-    cbp = torch.sign(cbp) * torch.sqrt(torch.abs(cbp) + 1e-10)      # :132
+    cbp = nl.signed_sqrt(cbp)                                       # :132
     return F.normalize(cbp)                                         # :133
 
 
@@ -203,6 +270,47 @@ def triuvec_bwd(g, dim):
     return out.reshape(B, dim, dim)
 
 
+class _CovpoolFn(torch.autograd.Function):
+    """Covpool as the reference defines it: its OWN backward formula (MPNCOV.py:121-134), not autograd's."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return covpool_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return covpool_bwd(x, g)
+
+
+class _SqrtmFn(torch.autograd.Function):
+    """Sqrtm with the reference's hand-derived backward (MPNCOV.py:166-202)."""
+
+    @staticmethod
+    def forward(ctx, x, iterN):
+        y, saved = sqrtm_fwd(x, iterN)
+        ctx.x, ctx.saved, ctx.iterN = x, saved, iterN
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return sqrtm_bwd(ctx.x, ctx.saved, g, ctx.iterN), None
+
+
+class _TriuvecFn(torch.autograd.Function):
+    """Triuvec with the reference's scatter backward (MPNCOV.py:220-230)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.dim = x.shape[1]
+        return triuvec_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return triuvec_bwd(g, ctx.dim)
+
+
 def mpncov_pool_fwd(x, iterN=5):
     """cov -> sqrtm -> triuvec on a [B,C,H,W] (already dimension-reduced) feature (MPNCOV.py:97-101)."""
     c = covpool_fwd(x)
@@ -242,15 +350,15 @@ def vgg_state_keys(cfg=VGG16_D):
     return keys
 
 
-def vgg_features_fwd(x, state, cfg=VGG16_D, prefix='backbone.'):
+def vgg_features_fwd(x, state, cfg=VGG16_D, prefix='backbone.', nl=Plain):
     """conv3x3(s1,p1)+bias -> ReLU, 'M' = MaxPool2d(2,2) (vgg.py:56-70)."""
     idx = 0
     for v in cfg:
         if v == 'M':
-            x = F.max_pool2d(x, 2, 2)
+            x = nl.maxpool(x, 2, 2)
             idx += 1
         else:
-            x = F.relu(F.conv2d(x, state[f'{prefix}{idx}.weight'], state[f'{prefix}{idx}.bias'], padding=1))
+            x = nl.relu(F.conv2d(x, state[f'{prefix}{idx}.weight'], state[f'{prefix}{idx}.bias'], padding=1))
             idx += 2
     return x
 
@@ -260,21 +368,21 @@ def cross_entropy_ls(logits, labels, smoothing=0.1):
     return F.cross_entropy(logits, labels, label_smoothing=smoothing)
 
 
-def bcnn_forward(x, state, stage=2, cfg=VGG16_D):
+def bcnn_forward(x, state, stage=2, cfg=VGG16_D, nl=Plain):
     """BCNN.forward (BCNN.py:49-55)."""
-    f = vgg_features_fwd(x, state, cfg)
+    f = vgg_features_fwd(x, state, cfg, nl=nl)
     if stage == 1:
         f = f.detach()
     y = bilinear_pool_fwd(f)
     return F.linear(y, state['classifier.weight'], state['classifier.bias'])
 
 
-def cbcnn_forward(x, state, output_dim, stage=2, cfg=VGG16_D):
+def cbcnn_forward(x, state, output_dim, stage=2, cfg=VGG16_D, nl=Plain):
     """CBCNN.forward (CBCNN.py:29-35)."""
-    f = vgg_features_fwd(x, state, cfg)
+    f = vgg_features_fwd(x, state, cfg, nl=nl)
     if stage == 1:
         f = f.detach()
-    y = cbp_fwd(f, output_dim)
+    y = cbp_fwd(f, output_dim, nl=nl)
     return F.linear(y, state['classifier.weight'], state['classifier.bias'])
 
 
@@ -308,33 +416,31 @@ def _bn_train(x, st, pre, eps=1e-5):
     return F.batch_norm(x, None, None, st[pre + '.weight'], st[pre + '.bias'], training=True, eps=eps)
 
 
-def _bottleneck(x, st, pre, stride, has_ds):
+def _bottleneck(x, st, pre, stride, has_ds, nl=Plain):
     """Bottleneck.forward (resnet.py:124-144): stride on the 3x3 (v1.5, :116)."""
-    out = F.relu(_bn_train(F.conv2d(x, st[pre + '.conv1.weight']), st, pre + '.bn1'))
-    out = F.relu(_bn_train(F.conv2d(out, st[pre + '.conv2.weight'], stride=stride, padding=1), st, pre + '.bn2'))
+    out = nl.relu(_bn_train(F.conv2d(x, st[pre + '.conv1.weight']), st, pre + '.bn1'))
+    out = nl.relu(_bn_train(F.conv2d(out, st[pre + '.conv2.weight'], stride=stride, padding=1), st, pre + '.bn2'))
     out = _bn_train(F.conv2d(out, st[pre + '.conv3.weight']), st, pre + '.bn3')
     identity = x
     if has_ds:
         identity = _bn_train(F.conv2d(x, st[pre + '.downsample.0.weight'], stride=stride), st, pre + '.downsample.1')
-    return F.relu(out + identity)
+    return nl.relu(out + identity)
 
 
-def resnet50_trunk_fwd(x, st, prefix='backbone.'):
+def resnet50_trunk_fwd(x, st, prefix='backbone.', nl=Plain):
     """children()[:-2] of ResNet-50 (MPNCOV.py:28-29): conv1, bn1, relu, maxpool, layer1..4 -> [B,2048,H/32,W/32]."""
     x = F.conv2d(x, st[prefix + '0.weight'], stride=2, padding=3)
-    x = F.relu(_bn_train(x, st, prefix + '1'))
-    x = F.max_pool2d(x, 3, 2, 1)
+    x = nl.relu(_bn_train(x, st, prefix + '1'))
+    x = nl.maxpool(x, 3, 2, 1)
     for li, (planes, blocks, stride) in enumerate(RESNET50_LAYERS):
         for b in range(blocks):
-            x = _bottleneck(x, st, f'{prefix}{4 + li}.{b}', stride if b == 0 else 1, b == 0)
+            x = _bottleneck(x, st, f'{prefix}{4 + li}.{b}', stride if b == 0 else 1, b == 0, nl=nl)
     return x
 
 
-def mpn_forward(x, st, iter_num=5):
+def mpn_forward(x, st, iter_num=5, nl=Plain):
     """MPN.forward (MPNCOV.py:33-38) with dimension_reduction (conv_dr_block, :64-69), is_sqrt, is_vec."""
-    f = resnet50_trunk_fwd(x, st)
-    f = F.relu(_bn_train(F.conv2d(f, st['pool.conv_dr_block.0.weight']), st, 'pool.conv_dr_block.1'))
-    c = covpool_fwd(f)
-    s, _ = sqrtm_fwd(c, iter_num)
-    v = triuvec_fwd(s)
+    f = resnet50_trunk_fwd(x, st, nl=nl)
+    f = nl.relu(_bn_train(F.conv2d(f, st['pool.conv_dr_block.0.weight']), st, 'pool.conv_dr_block.1'))
+    v = _TriuvecFn.apply(_SqrtmFn.apply(_CovpoolFn.apply(f), iter_num))            # MPNCOV.py:97-101
     return F.linear(v.reshape(v.shape[0], -1), st['classifier.weight'], st['classifier.bias'])

@@ -1,6 +1,7 @@
 """CPU-side checks of the C-ABI boundary: the library loads and exports every symbol the header declares."""
 import ctypes
 import os
+import re
 
 
 def test_library_exports_every_declared_symbol():
@@ -12,9 +13,8 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     missing = [n for n in protos if not hasattr(lib, n)]
     assert not missing, missing
-    assert b'sm_100a' in lib.hk_version.__call__.__self__.restype.__name__.encode() or True
     lib.hk_version.restype = ctypes.c_char_p
-    assert b'hawkeye_b200' in lib.hk_version()
+    assert b'hawkeye_b200' in lib.hk_version() and b'sm_100a' in lib.hk_version()
 
 
 def test_no_fallback_when_library_missing(monkeypatch, tmp_path):
@@ -40,4 +40,5 @@ def test_product_does_not_import_oracle():
         for f in fs:
             if f.endswith('.py'):
                 src = open(os.path.join(dp, f)).read()
-                assert 'oracle' not in src.replace('no oracle', ''), f
+                assert not re.search(r'^\s*(from|import)\s+\S*oracle|__import__\([^)]*oracle|import_module\([^)]*oracle', src,
+                                     flags=re.M), f
