@@ -74,5 +74,11 @@ def resnet50(pretrained=False, progress=True, **kwargs):
             head = k.split('.')[0]
             if head in names:
                 remap[str(names.index(head)) + k[len(head):]] = v
-        trunk.load_state_dict(remap)
+        trunk.load_state_dict(remap)           # strict: every trunk tensor must be present (fc.* is not part of the trunk)
+    elif pretrained and os.environ.get('HAWKEYE_ALLOW_RANDOM_INIT', '0') != '1':
+        import logging
+        logging.getLogger('hawkeye_b200').warning(
+            'resnet50(pretrained=True): no checkpoint at $HAWKEYE_RESNET50_PTH (%r) — the trunk keeps the reference\'s '
+            'RANDOM initialisation.  Point HAWKEYE_RESNET50_PTH at torchvision\'s resnet50 .pth, or set '
+            'HAWKEYE_ALLOW_RANDOM_INIT=1 (benchmarks / parity tests) to silence this.', path)
     return trunk

@@ -56,4 +56,11 @@ def vgg16(pretrained=False, progress=True, **kwargs):
     if pretrained and path and os.path.exists(path):
         sd = torch.load(path, map_location='cpu')
         feats.load_state_dict({k[len('features.'):]: v for k, v in sd.items() if k.startswith('features.')})
+    elif pretrained and os.environ.get('HAWKEYE_ALLOW_RANDOM_INIT', '0') != '1':
+        # the reference downloads ImageNet weights here (vgg.py:83-85); silently training on a random VGG would be wrong
+        import logging
+        logging.getLogger('hawkeye_b200').warning(
+            'vgg16(pretrained=True): no checkpoint at $HAWKEYE_VGG16_PTH (%r) — the backbone keeps the reference\'s RANDOM '
+            'initialisation.  Point HAWKEYE_VGG16_PTH at torchvision\'s vgg16 .pth, or set HAWKEYE_ALLOW_RANDOM_INIT=1 '
+            '(benchmarks / parity tests) to silence this.', path)
     return feats

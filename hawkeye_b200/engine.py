@@ -77,8 +77,8 @@ class FusedSGD:
         self.defaults = dict(lr=lr, momentum=momentum, weight_decay=weight_decay)
         self.param_groups = []
         for gi, g in enumerate(flat.groups):
-            self.param_groups.append(dict(params=g, lr=(group_lrs[gi] if group_lrs else lr), momentum=momentum,
-                                          weight_decay=weight_decay, initial_lr=lr))
+            glr = group_lrs[gi] if group_lrs else lr
+            self.param_groups.append(dict(params=g, lr=glr, momentum=momentum, weight_decay=weight_decay, initial_lr=glr))
         self.first = True
         self.grad_scale = 1.0
         self.state = {}
@@ -131,12 +131,15 @@ class FusedAdam:
                       float(pg['weight_decay']), float(self.grad_scale), self.t, s)
 
     def state_dict(self):
-        return dict(m=self.m, v=self.v, t=self.t)
+        return dict(m=self.m, v=self.v, t=self.t, param_groups=[{k: v for k, v in g.items() if k != 'params'}
+                                                                for g in self.param_groups])
 
     def load_state_dict(self, sd):
         self.m.copy_(sd['m'])
         self.v.copy_(sd['v'])
         self.t = sd['t']
+        for g, s in zip(self.param_groups, sd.get('param_groups', [])):     # lr reduced by a plateau scheduler survives
+            g.update(s)
 
 
 # ----------------------------------------------------------------------------------------------------------

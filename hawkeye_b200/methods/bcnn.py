@@ -21,6 +21,7 @@ class BCNN(nn.Module):
         self.stage = config.stage if 'stage' in config else 2          # BCNN.py:36
         self.backbone = vgg16(pretrained=True)                           # BCNN.py:38-39 (all 31 feature layers)
         self.bilinear_pooling = BilinearPooling()
+        ops.check_num_classes(config.num_classes)
         self.classifier = nn.Linear(self.backbone.out_channels ** 2, config.num_classes)
         self.classifier.apply(initialize_weights)
         if self.stage == 1:                                              # BCNN.py:45-47

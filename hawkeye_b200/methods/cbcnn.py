@@ -52,6 +52,7 @@ class CBCNN(nn.Module):
         in_channel, out_channel = config.input_channel, config.output_channel   # CBCNN.py:18-19
         self.backbone = vgg16(pretrained=True)
         self.bilinear_pooling = CompactBilinearPooling(in_channel, in_channel, out_channel)
+        ops.check_num_classes(config.num_classes)
         self.classifier = nn.Linear(out_channel, config.num_classes)
         self.classifier.apply(initialize_weights)
         self.backbone.train_backbone = config.stage != 1

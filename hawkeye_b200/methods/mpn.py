@@ -28,7 +28,7 @@ class MPNCOV(nn.Module):
         if self.dr is not None:
             u = self._dr_unit
             ps = u.params()
-            save = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in ps)
+            save = ops_resnet._wants_grad(x, ps, self.training, 'MPNCOV.conv_dr_block')
             x = ops_resnet.DRBlockFn.apply(x, u, save, self.training, *ps)
         x = ops.CovpoolLayer(x)
         if self.is_sqrt:
@@ -44,6 +44,7 @@ class MPN(nn.Module):
         super().__init__()
         self.backbone = resnet50(pretrained=True)                          # MPNCOV.py:28-29
         self.pool = MPNCOV(config.iter_num, config.is_sqrt, config.is_vec, config.input_dim, config.dimension_reduction)
+        ops.check_num_classes(config.num_classes)
         self.classifier = nn.Linear(self.pool.output_dim, config.num_classes)
 
     def forward(self, x):

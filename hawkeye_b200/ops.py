@@ -104,6 +104,14 @@ def linear(x, w, b):
     return LinearFn.apply(x, w, b)
 
 
+def check_num_classes(n):
+    """The classifier's dgrad / wgrad GEMMs take dlogits [B, num_classes] through TMA, whose row pitch must be a multiple
+    of 16 bytes: fail at model construction with a clear message instead of in the first backward."""
+    if int(n) % 4 != 0:
+        raise _lib.HawkeyeLibError(f'num_classes={n}: hawkeye_b200 classifiers need num_classes % 4 == 0 (16-byte TMA row '
+                                   'pitch of the logit gradients); pad the label space to the next multiple of 4')
+
+
 # ----------------------------------------------------------------------------------------------------------
 # CrossEntropyLoss(label_smoothing) (train.py:211-212)
 # ----------------------------------------------------------------------------------------------------------
@@ -248,7 +256,9 @@ class VGGFeaturesFn(Function):
 
 
 def vgg_features(x, cfg, params, train_backbone=True):
-    save = bool(train_backbone) and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    """``train_backbone`` is kept for call compatibility; whether activations are saved for backward is decided from what
+    actually requires grad at call time (so freezing / unfreezing the backbone after construction just works)."""
+    save = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
     return VGGFeaturesFn.apply(x, tuple(cfg), save, *params)
 
 

@@ -255,8 +255,19 @@ def resnet_trunk(x, trunk_module):
     plan = trunk_module._plan
     params = plan.params()
     training = trunk_module.training
-    save = training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    save = _wants_grad(x, params, training, 'ResNet trunk')
     return ResNetTrunkFn.apply(x, plan, save, training, *params)
+
+
+def _wants_grad(x, params, training, what):
+    """Save-for-backward decision, taken from what requires grad at call time.  Gradients through EVAL-mode BatchNorm
+    (running statistics) are not on the reference's training path and have no kernel here: asking for them is an error,
+    never a silent None."""
+    want = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+    if want and not training:
+        raise _lib.HawkeyeLibError(f'{what}: backward through eval-mode BatchNorm is not implemented — call .train(), '
+                                   'or run under torch.no_grad() / with all inputs and parameters frozen')
+    return want
 
 
 class DRBlockFn(Function):

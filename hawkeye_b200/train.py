@@ -79,6 +79,8 @@ class Trainer:
         torch.cuda.set_device(self.device)
         if 'seed' in self.config.experiment and self.config.experiment.seed is not None:
             torch.manual_seed(self.config.experiment.seed)
+        self.samplers = {}
+        # user-supplied dataloaders must already be rank-sharded when world > 1 (e.g. built with a DistributedSampler)
         self.dataloaders = dataloaders if dataloaders is not None else self.get_dataloader(self.config.dataset)
         self.model = self.get_model(self.config.model)
         self.model = self.to_device(self.model, parallel=True)
@@ -119,8 +121,25 @@ class Trainer:
               'val': ClassificationPresetEval(crop_size=t['image_size'], resize_size=resize)}
         ds = {s: FGDataset(config.root_dir, os.path.join(config.meta_dir, s + '.txt'), transform=tf[s])
               for s in ('train', 'val')}
-        return {s: DataLoader(ds[s], config.batch_size, num_workers=config.num_workers, pin_memory=True,
-                              shuffle=s == 'train') for s in ('train', 'val')}
+        # One process per GPU replaces nn.DataParallel (train.py:220-228), which SPLITS config.batch_size across the visible
+        # GPUs: batch_size stays the GLOBAL batch, each rank draws batch_size / world images from its own shard of the
+        # training set (DistributedSampler, reshuffled per epoch in train()); validation is sharded the same way and the
+        # accuracy meters are reduced over ranks in validate().
+        if config.batch_size % self.world != 0:
+            raise ValueError(f'dataset.batch_size={config.batch_size} must be a multiple of the {self.world} ranks')
+        per_rank = config.batch_size // self.world
+        self.samplers = {}
+        loaders = {}
+        for s in ('train', 'val'):
+            sampler = None
+            if self.world > 1:
+                from torch.utils.data.distributed import DistributedSampler
+                sampler = DistributedSampler(ds[s], num_replicas=self.world, rank=self.rank, shuffle=s == 'train',
+                                             drop_last=False)
+            self.samplers[s] = sampler
+            loaders[s] = DataLoader(ds[s], per_rank, num_workers=config.num_workers, pin_memory=True, sampler=sampler,
+                                    shuffle=(s == 'train' and sampler is None))
+        return loaders
 
     def get_criterion(self, config):
         return ops.CrossEntropyLS(label_smoothing=0.1)              # train.py:211-212
@@ -244,6 +263,12 @@ class Trainer:
             m.reset()
         for data in self.dataloaders['val']:
             self.batch_validate(data)
+        if self.world > 1:                      # every rank saw its own shard: reduce (sum, count) of each meter over ranks
+            import torch.distributed as dist
+            for m in self.average_meters.values():
+                t = torch.tensor([m.sum, m.count], dtype=torch.float64, device=self.device)
+                dist.all_reduce(t)
+                m.sum, m.count = t[0].item(), int(t[1].item())
         self.model.train(True)
 
     def train(self):
@@ -255,6 +280,8 @@ class Trainer:
             for m in self.average_meters.values():
                 m.reset()
             self.on_start_epoch(None)
+            if self.samplers.get('train') is not None:
+                self.samplers['train'].set_epoch(epoch)
             for data in self.dataloaders['train']:
                 self.on_start_forward(None)
                 self.batch_training(data)
@@ -277,7 +304,11 @@ class Trainer:
         else:
             self.scheduler.step()
 
-    # ---- checkpoint formats identical to the reference (train.py:369-395): plain state_dict .pth ---------------------
+    # ---- checkpoints (train.py:369-395).  save_model writes the reference's format exactly (a plain model state_dict
+    # .pth; reference-trained files load through load_state_dict and vice versa).  save_checkpoint keeps the reference's
+    # top-level layout {'epoch','model','optimizer','scheduler'} with an identical 'model' part, but the optimizer /
+    # scheduler parts are the fused optimizers' own state (flat momentum / Adam moments), not torch.optim's: a reference
+    # checkpoint resumes here with its model weights only (load_checkpoint says so instead of failing). -----------------
     def save_model(self, name=None):
         os.makedirs(self.log_root, exist_ok=True)
         path = os.path.join(self.log_root, name or f'{self.config.model.name}_epoch_{self.epoch + 1}.pth')
@@ -296,8 +327,13 @@ class Trainer:
         ck = torch.load(path, map_location='cpu')
         self.start_epoch = ck['epoch']
         load_state_dict(self.model, ck['model'])
-        self.optimizer.load_state_dict(ck['optimizer'])
-        self.scheduler.load_state_dict(ck['scheduler'])
+        opt = ck.get('optimizer', {})
+        if isinstance(opt, dict) and ('buf' in opt or 'm' in opt):
+            self.optimizer.load_state_dict(opt)
+            self.scheduler.load_state_dict(ck['scheduler'])
+        else:
+            self.logger.warning('checkpoint %s carries torch.optim state (a reference checkpoint): model weights and epoch '
+                                'restored, optimizer / scheduler state re-initialised', path)
 
     def on_start_epoch(self, config):
         pass

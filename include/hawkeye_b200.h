@@ -6,9 +6,8 @@
  *     >0 = cudaError_t from a launch.  hk_last_error() gives the text (thread-local).
  *   - the caller owns every device buffer including workspaces (query *_workspace_bytes);
  *     the library allocates nothing and never synchronises; all work is enqueued on `stream`
- *     (a cudaStream_t passed as void*).  The only library-owned device state is a 1 MB static table of
- *     launch-tagged words used by hk_bilinear_pool_fwd for its cross-CTA norm exchange (8 regions handed
- *     out round-robin per call, so up to 8 calls may be in flight on different streams).
+ *     (a cudaStream_t passed as void*).  There is no library-owned device state: every entry point is re-entrant and
+ *     may run concurrently with anything else on the GPU (no kernel waits on another thread-block cluster).
  *   - tensors are contiguous fp32; pointers 16-byte aligned; no CPU fallback: an unsupported
  *     shape is an error (-3), never a silent slow path.
  * Each entry point cites the reference interface it replaces (paths relative to the Hawkeye tree).
@@ -52,9 +51,6 @@ int hk_gemm_tf32(const float* A, int a_mn_major, long long lda, long long stride
  * x [B,C,HW] (NCHW feature map viewed as in BCNN.py:17) -> y [B,C*C] = normalize(sqrt(x x^T/HW + 1e-5)).
  * inv_norm_out (optional, [B]) receives 1/||z||.  Requires C%128==0, HW%4==0. */
 size_t hk_bilinear_pool_fwd_workspace_bytes(int B, int C, int HW);
-/* profiling aid (no reference counterpart): per-CTA %globaltimer stamps of the following hk_bilinear_pool_fwd launches are
- * written to buf ([148][16] unsigned long long, device memory); NULL switches it off. */
-void hk_debug_gram_trace(void* buf);
 int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, int C, int HW, void* workspace,
                          size_t workspace_bytes, void* stream);
 /* backward of the same (what autograd derives for BCNN.py:13-27): dx [B,C,HW] from dy [B,C*C]; z is recomputed.

@@ -11,6 +11,12 @@ import torch
 import torch.nn.functional as F
 
 
+def rel_l2(a, b):
+    a = torch.as_tensor(a).double().flatten()
+    b = torch.as_tensor(b).double().flatten()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
 def _nchw(t):
     return t.permute(0, 3, 1, 2)
 
@@ -68,7 +74,6 @@ def oracle_step(forward_fn, x, labels, state, items, train_keys):
 
 
 def compare_grads(gpu_grads, ref_grads, tol, what=''):
-    from conftest import rel_l2
     errs = {k: rel_l2(g, ref_grads[k]) for k, g in gpu_grads.items()}
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
     print(f'{what}: {len(errs)} parameter gradients, worst rel-L2: ' + ', '.join(f'{k} {v:.2e}' for k, v in worst))

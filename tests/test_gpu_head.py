@@ -27,17 +27,23 @@ def test_linear(B, Fdim, N):
     assert max(errs[:3]) < 2e-3 and errs[3] < 1e-5
 
 
-def test_cross_entropy_ls():
-    from hawkeye_b200 import ops
+@pytest.mark.parametrize('precise', [0, 1])
+def test_cross_entropy_ls(precise):
+    """default mode: dlogits are rounded to tf32 on store (operand of the classifier MMAs) -> 2^-12 rms; precise: fp32"""
+    from hawkeye_b200 import ops, _lib
     logits = detgen.det((32, 200), 1)
     labels = detgen.det_labels(32, 200, 2)
     lg = logits.cuda().requires_grad_(True)
-    loss = ops.CrossEntropyLS(0.1)(lg, labels.cuda())
-    (g,) = torch.autograd.grad(loss, lg)
+    _lib.set_precise(precise)
+    try:
+        loss = ops.CrossEntropyLS(0.1)(lg, labels.cuda())
+        (g,) = torch.autograd.grad(loss, lg)
+    finally:
+        _lib.set_precise(0)
     ld = logits.double().requires_grad_(True)
     ref = F.cross_entropy(ld, labels, label_smoothing=0.1)
     (rg,) = torch.autograd.grad(ref, ld)
-    assert abs(loss.item() - ref.item()) < 1e-5 and rel_l2(g.cpu(), rg) < 1e-5
+    assert abs(loss.item() - ref.item()) < 1e-5 and rel_l2(g.cpu(), rg) < (1e-5 if precise else 3e-4)
 
 
 def test_sgd_and_adam():

