@@ -1,12 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the BCNN VGG-16 448x448 train step (BASELINE.json metric) on N B200s, one process per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--stage 2] [--batch 32] [--impl native|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload bcnn_s2|bcnn_s1|cbcnn8192|mpn] [--batch 32]
+                  [--impl native|reference]
 
-Prints ONE JSON line (rank 0).  `value` = device-timed images/s with inputs resident in HBM; `e2e` = the same step
-through hawkeye_b200.train.Trainer.batch_training with pinned HOST inputs (H2D copy + loss/acc read-back inside the
-timed region); `roofline` = the fused bilinear-pool forward (hk_bilinear_pool_fwd) against the measured HBM peak;
-`cpu_baseline` = the oracle port of the same step on the host cores.  `--impl reference` times that CPU path only.
+Prints ONE JSON line (rank 0).
+  value         device-timed images/s, inputs resident in HBM (CUDA events, max over ranks)
+  e2e           the same step through hawkeye_b200.train.Trainer.batch_training with pinned HOST inputs (H2D copy and the
+                loss / accuracy read-back inside the timed region)
+  roofline      hk_bilinear_pool_fwd (K1, the kernel BASELINE.json names) against the measured HBM peak, at the workload's
+                batch 32 and at 256 / 1024; roofline_bwd = hk_bilinear_pool_bwd (K1b); roofline_cbp = hk_cbp_fwd (K2);
+                roofline_mpncov = covariance + Newton-Schulz fwd+bwd (K3/K4) against the TF32 tensor peak
+  roofline_conv whole-step TF32 TFLOP/s against measured bf16-sustained / 2
+  eager_gpu     informational: the same BCNN step in stock PyTorch eager (torch.nn, cuDNN/cuBLAS with TF32 allowed) on the
+                same GPU — the practical bar, not the reference arm
+  cpu_baseline  the reference step on the host cores: the UNMODIFIED reference when its tree is importable
+                ($HAWKEYE_REF, baseline/_ref, /root/reference; kind "reference"), else the oracle port (kind "port")
+`--impl reference` times that CPU path only and reports the steps it actually timed.
 """
 import argparse
 import json
@@ -22,14 +32,26 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 import torch  # noqa: E402
 
-K1_FWD_BYTES_PER_IMG = 1449984      # read X 512*196*4 + write Y 512*512*4 (SURVEY.md §8(d))
-K1_BWD_BYTES_PER_IMG = 1851392
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of bcnn_gram_fwd_kernel from the ncu --set full captures
-# summarised in profiles/gram_r1h_metrics.txt (tests/prof_bilinear.py 32 / 256)
-K1_DRAM_TRAFFIC_B32 = 12.89e6
-K1_DRAM_TRAFFIC_B256 = 102.85e6 + 208.88e6
+K1_FWD_BYTES_PER_IMG = 1449984      # read X 512*196*4 + write Y 512*512*4 (SURVEY.md 8(d))
+K1_BWD_BYTES_PER_IMG = 1851392      # read dY + read X + write dX (z recomputed)
 VGG16_FWD_GFLOP_PER_IMG = 122.9
-METRIC = '448x448 images/sec, BCNN VGG-16 train step (fwd+CE+bwd+grad all-reduce+SGD), device-timed, max over ranks'
+RESNET50_MPN_FWD_GFLOP_PER_IMG = 32.9
+MPNCOV_GFLOP_PER_IMG = 1.77         # covariance + 5-iteration Newton-Schulz, forward + backward
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/ (see
+# profiles/README.md for the file each number comes from); None = not captured for this build
+K1_DRAM_TRAFFIC = {32: None, 256: None}
+WORKLOADS = {
+    'bcnn_s2': dict(cfg='BCNN_S2.yaml', trainer='BCNN', model='BCNN VGG-16 stage 2', fwd_gflop=VGG16_FWD_GFLOP_PER_IMG, bwd_mult=3.0),
+    'bcnn_s1': dict(cfg='BCNN_S1.yaml', trainer='BCNN', model='BCNN VGG-16 stage 1 (classifier only)', fwd_gflop=VGG16_FWD_GFLOP_PER_IMG, bwd_mult=1.0),
+    'cbcnn8192': dict(cfg='CBCNN_S1.yaml', trainer='CBCNN', model='CBCNN VGG-16 d=8192 stage 1', fwd_gflop=VGG16_FWD_GFLOP_PER_IMG, bwd_mult=1.0),
+    'mpn': dict(cfg='MPN.yaml', trainer='MPN', model='Fast MPN-COV ResNet-50', fwd_gflop=RESNET50_MPN_FWD_GFLOP_PER_IMG, bwd_mult=3.0),
+}
+
+
+def metric_name(w):
+    if w == 'bcnn_s2':
+        return '448x448 images/sec, BCNN VGG-16 train step (fwd+CE+bwd+grad all-reduce+SGD), device-timed, max over ranks'
+    return f'448x448 images/sec, {WORKLOADS[w]["model"]} train step (fwd+CE+bwd+grad all-reduce+optimizer), device-timed, max over ranks'
 
 
 def measured_peaks():
@@ -86,54 +108,156 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def host_threads():
-    """Threads for the CPU arm: all cores up to 32 (a batch-2 step stops scaling, and oversubscribes, beyond that)."""
-    return max(1, min(os.cpu_count() or 1, 32))
-
-
-def cpu_step_port(stage, B, threads, steps):
-    """The oracle port of the reference step on the host cores (test/bench infrastructure, never the product)."""
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference step on the host cores
+# ----------------------------------------------------------------------------------------------------------------------
+def _cpu_state_and_forward(workload):
+    """(state dict, forward(x, state), trainable keys) of the oracle port for `workload`."""
     import detgen
     from oracle import hop_oracle as O
+    if workload in ('bcnn_s1', 'bcnn_s2'):
+        stage = 1 if workload == 'bcnn_s1' else 2
+        state = detgen.vgg_bcnn_state(O.VGG16_D, 200, seed=100)
+        keys = None if stage == 2 else {'classifier.weight', 'classifier.bias'}
+        return state, (lambda xx, st: O.bcnn_forward(xx, st, stage)), keys
+    if workload == 'cbcnn8192':
+        state = detgen.vgg_bcnn_state(O.VGG16_D, 200, seed=100, head_in=8192)
+        return state, (lambda xx, st: O.cbcnn_forward(xx, st, 8192, 1)), {'classifier.weight', 'classifier.bias'}
+    import hawkeye_b200 as hb
+
+    class Cfg(dict):
+        __getattr__ = dict.__getitem__
+    net = hb.MODEL.get('MPN')(Cfg(name='MPN', iter_num=5, is_sqrt=True, is_vec=True, input_dim=2048,
+                                  dimension_reduction=256, num_classes=200))
+    state = detgen.state_like(net)
+    keys = {k for k, _ in net.named_parameters()}
+    return state, (lambda xx, st: O.mpn_forward(xx, st, 5)), keys
+
+
+def cpu_step_port(workload, B, threads, steps):
+    """The oracle port of the reference step (test/bench infrastructure, never the product)."""
+    from oracle import hop_oracle as O
     torch.set_num_threads(threads)
-    state = detgen.vgg_bcnn_state(O.VGG16_D, 200, seed=100)
-    keys = None if stage == 2 else {'classifier.weight', 'classifier.bias'}
+    state, fwd, keys = _cpu_state_and_forward(workload)
     x = torch.randn(B, 3, 448, 448, generator=torch.Generator().manual_seed(1234))
     labels = torch.randint(0, 200, (B,), generator=torch.Generator().manual_seed(1))
     bufs = {}
 
     def step():
-        _, loss, grads = O.loss_and_grads(lambda xx, st: O.bcnn_forward(xx, st, stage), x, labels, state, keys)
+        _, loss, grads = O.loss_and_grads(fwd, x, labels, state, keys)
         for k, g in grads.items():
-            state[k], bufs[k] = O.sgd_momentum_step(state[k], g, bufs.get(k), 0.005, 0.9, 1e-5, k not in bufs)
+            if g is not None:
+                state[k], bufs[k] = O.sgd_momentum_step(state[k], g, bufs.get(k), 0.005, 0.9, 1e-5, k not in bufs)
         return loss
 
     step()  # warm-up
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
-    dt = (time.perf_counter() - t0) / steps
-    return B / dt, dt
+    return (time.perf_counter() - t0) / steps
+
+
+def cpu_step_reference(workload, B, threads, steps):
+    """The UNMODIFIED reference (model/registry.MODEL + nn.CrossEntropyLoss(label_smoothing=0.1) + torch.optim, i.e. what
+    train.py:310-325 runs) imported from $HAWKEYE_REF / baseline/_ref / /root/reference.  Raises if the tree is absent."""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        raise RuntimeError('reference tree not importable')
+    rh.load_reference()
+    from model.registry import MODEL
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    if workload in ('bcnn_s1', 'bcnn_s2'):
+        net = MODEL.get('BCNN')(rh.cfg(name='BCNN', stage=1 if workload == 'bcnn_s1' else 2, num_classes=200))
+    elif workload == 'cbcnn8192':
+        net = MODEL.get('CBCNN')(rh.cfg(name='CBCNN', stage=1, num_classes=200, input_channel=512, output_channel=8192))
+        for p in net.backbone.parameters():                          # Examples/CBCNN.py:13-15
+            p.requires_grad = False
+    else:
+        net = MODEL.get('MPN')(rh.cfg(name='MPN', iter_num=5, is_sqrt=True, is_vec=True, input_dim=2048,
+                                      dimension_reduction=256, num_classes=200))
+    net.train()
+    params = [p for p in net.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=0.005, momentum=0.9, weight_decay=1e-5) if workload != 'mpn' else \
+        torch.optim.Adam(params, lr=8e-5, weight_decay=2e-5)
+    crit = torch.nn.CrossEntropyLoss(label_smoothing=0.1)
+    x = torch.randn(B, 3, 448, 448, generator=torch.Generator().manual_seed(1234))
+    labels = torch.randint(0, 200, (B,), generator=torch.Generator().manual_seed(1))
+
+    def step():
+        loss = crit(net(x), labels)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps
+
+
+def cpu_baseline(workload, steps):
+    """-> dict(value img/s, cores, kind, sample, dt).  Batch 2 (BASELINE.json configs[0]); all host threads it can use:
+    a batch-2 step stops scaling around 32 threads, so 32 and os.cpu_count() are both probed and the faster one is kept."""
+    B = 2
+    ncpu = os.cpu_count() or 1
+    for fn, kind in ((cpu_step_reference, 'reference'), (cpu_step_port, 'port')):
+        try:
+            cands = sorted({min(32, ncpu), ncpu})
+            best = None
+            for th in cands:
+                dt = fn(workload, B, th, 1)
+                if best is None or dt < best[1]:
+                    best = (th, dt)
+            threads = best[0]
+            dt = fn(workload, B, threads, steps) if steps > 1 else best[1]
+            what = ('UNMODIFIED reference modules (model.registry.MODEL) + torch.optim' if kind == 'reference'
+                    else 'torch-CPU oracle port of the reference step')
+            return dict(value=B / dt, unit='img/s', cores=threads, kind=kind, dt=dt,
+                        sample=f'{max(steps, 1)} timed step(s) of batch {B} ({dt:.2f} s/step; fwd+CE+bwd+optimizer), {what}, '
+                               f'{threads} of {ncpu} host threads')
+        except Exception as e:  # reference tree absent on the GPU box -> port
+            last = e
+    raise last
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    threads = host_threads()
-    B = 2
-    ips, dt = cpu_step_port(args.stage, B, threads, max(1, min(args.steps, 3)))
+    timed = max(1, min(args.steps, 3))
+    cb = cpu_baseline(args.workload, timed)
+    dt = cb.pop('dt')
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'img/s', 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'BCNN VGG-16 stage {args.stage}, 448x448, 200 classes; CPU sample batch {B}'},
-        'cpu_baseline': {'value': ips, 'unit': 'img/s', 'cores': threads, 'kind': 'port',
-                         'sample': f'{min(args.steps, 3)} timed steps of batch {B} (fwd+CE+bwd+SGD), torch-CPU oracle '
-                                   f'port of the reference step, {threads} threads'},
-        'e2e': {'value': ips, 'unit': 'img/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'impl': 'reference', 'metric': metric_name(args.workload), 'value': cb['value'], 'unit': 'img/s', 'n_gpus': args.gpus,
+        'steps': timed, 'steps_requested': args.steps, 'warmup': 1, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{WORKLOADS[args.workload]["model"]}, 448x448, 200 classes; CPU sample batch 2 '
+                               f'(BASELINE.json configs[0])'},
+        'cpu_baseline': cb,
+        'e2e': {'value': cb['value'], 'unit': 'img/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# kernel micro-benchmarks (rank 0, one GPU)
+# ----------------------------------------------------------------------------------------------------------------------
+def _timed_calls(call, nset, reps):
+    for i in range(min(nset, 3)):
+        call(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(int(4e6))        # ~2 ms of device-side spin so the host enqueues ahead of the GPU (no launch gaps)
+    e0.record()
+    for _ in range(reps):
+        for i in range(nset):
+            call(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / (reps * nset)
 
 
 def time_bilinear_kernel(B, bwd=False, min_footprint=640 << 20, reps=4):
@@ -161,18 +285,100 @@ def time_bilinear_kernel(B, bwd=False, min_footprint=640 << 20, reps=4):
         else:
             _lib.call(name, xs[i], ys[i], None, B, 512, 196, ws, nb, s)
 
-    for i in range(min(nset, 3)):
-        call(i)
+    return _timed_calls(call, nset, reps)
+
+
+def time_cbp_kernel(B, d=8192, min_footprint=640 << 20, reps=4):
+    """hk_cbp_fwd (K2): algorithmic traffic 401 408 B in + 4 d B out per image."""
+    import numpy as np
+    from hawkeye_b200 import _lib, ops
+    per_set = B * (401408 + 8 * d)
+    nset = max(2, min(64, -(-min_footprint // per_set)))
+    h1, s1, h2, s2 = ops.count_sketch_hashes(512, d)
+    dev = 'cuda'
+    h1, h2 = torch.from_numpy(h1.astype(np.int32)).to(dev), torch.from_numpy(h2.astype(np.int32)).to(dev)
+    s1, s2 = torch.from_numpy(s1.astype(np.float32)).to(dev), torch.from_numpy(s2.astype(np.float32)).to(dev)
+    xs = [torch.rand(B, 512, 14, 14, device=dev) for _ in range(nset)]
+    ys = [torch.empty(B, d, device=dev) for _ in range(nset)]
+    pres = [torch.empty(B, d, device=dev) for _ in range(nset)]
+    s = _lib.stream_ptr()
+    return _timed_calls(lambda i: _lib.call('hk_cbp_fwd', xs[i], h1, h2, s1, s2, ys[i], pres[i], B, 512, 196, d, s), nset, reps)
+
+
+def time_mpncov_head(B, reps=3):
+    """covariance pooling + 5-iteration Newton-Schulz + triu-vec, forward + backward, on [B,256,14,14] (K3/K4)."""
+    from hawkeye_b200 import ops
+    x = torch.rand(B, 256, 14, 14, device='cuda', requires_grad=True)
+
+    def fb():
+        v = ops.TriuvecLayer(ops.SqrtmLayer(ops.CovpoolLayer(x), 5))
+        v.backward(torch.ones_like(v))
+        x.grad = None
+
+    for _ in range(2):
+        fb()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda._sleep(int(4e6))        # ~2 ms of device-side spin so the host enqueues ahead of the GPU (no launch gaps)
     e0.record()
     for _ in range(reps):
-        for i in range(nset):
-            call(i)
+        fb()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e-3 / (reps * nset)
+    return e0.elapsed_time(e1) * 1e-3 / reps
+
+
+def eager_gpu_bcnn(stage, B, steps):
+    """Stock PyTorch eager on this GPU: torch.nn VGG-16 'D' features + the reference's BilinearPooling arithmetic +
+    nn.Linear, CE(label_smoothing=0.1), SGD(momentum) — cuDNN / cuBLAS kernels with TF32 allowed.  Informational."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    layers, cin = [], 3
+    for v in [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M']:
+        if v == 'M':
+            layers.append(nn.MaxPool2d(2, 2))
+        else:
+            layers += [nn.Conv2d(cin, v, 3, padding=1), nn.ReLU(inplace=True)]
+            cin = v
+    feats = nn.Sequential(*layers).cuda()
+    cls = nn.Linear(512 * 512, 200).cuda()
+    if stage == 1:
+        for p in feats.parameters():
+            p.requires_grad = False
+    params = [p for p in list(feats.parameters()) + list(cls.parameters()) if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=0.005, momentum=0.9, weight_decay=1e-5)
+    x = torch.randn(B, 3, 448, 448, device='cuda')
+    y = torch.randint(0, 200, (B,), device='cuda')
+
+    def step():
+        f = feats(x)
+        if stage == 1:
+            f = f.detach()
+        f = f.view(B, 512, -1)
+        g = torch.bmm(f, f.transpose(1, 2)) / f.shape[2]                 # BCNN.py:17-18
+        z = F.normalize(torch.sqrt(g.view(B, -1) + 1e-5))                # BCNN.py:21,26
+        loss = F.cross_entropy(cls(z), y, label_smoothing=0.1)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del feats, cls, opt
+    torch.cuda.empty_cache()
+    return dict(value=B / ms * 1e3, unit='img/s', ms_per_step=ms,
+                note='stock PyTorch eager (torch.nn + cuDNN/cuBLAS, allow_tf32=True, cudnn.benchmark) on the same GPU, same '
+                     'batch; informational practical bar, not the reference arm')
 
 
 def main():
@@ -180,26 +386,32 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--stage', type=int, default=2)
+    ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS))
+    ap.add_argument('--stage', type=int, default=2, help='BCNN stage (kept for compatibility; --workload wins)')
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--impl', default='native')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs only')
+    ap.add_argument('--no-micro', action='store_true', help='skip the kernel micro-benchmarks (roofline legs)')
+    ap.add_argument('--no-eager', action='store_true', help='skip the stock-PyTorch eager GPU leg')
     args = ap.parse_args()
+    if args.workload is None:
+        args.workload = f'bcnn_s{args.stage}'
     if args.impl == 'reference':
         return run_reference_arm(args)
 
     import torch.distributed as dist
-    from hawkeye_b200 import _lib, engine
+    from hawkeye_b200 import _lib, engine, examples
     from hawkeye_b200.config import load_config
-    from hawkeye_b200.train import Trainer
 
+    os.environ.setdefault('HAWKEYE_ALLOW_RANDOM_INIT', '1')     # random-init weights are the benchmark's contract
+    W = WORKLOADS[args.workload]
     rank, local, world = engine.init_distributed()
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    cfg = load_config(os.path.join(ROOT, 'configs', f'BCNN_S{args.stage}.yaml'))
+    cfg = load_config(os.path.join(ROOT, 'configs', W['cfg']))
     torch.manual_seed(0)                                   # random-init weights, reference initialisers
-    tr = Trainer(cfg, dataloaders={})
+    tr = examples.TRAINERS[W['trainer']](cfg, dataloaders={})
     tr.model.train()
     B = args.batch
     g = torch.Generator().manual_seed(1234 + rank)
@@ -234,7 +446,8 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         loss = step_resident()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
@@ -262,50 +475,65 @@ def main():
             dist.destroy_process_group()
         return
     hbm_peak, tf_peak, which = measured_peaks()
-    if args.no_e2e:
-        t_avg, t256, t1024 = float('nan'), float('nan'), float('nan')
-    else:
-        t_avg = time_bilinear_kernel(32)
-        t256 = time_bilinear_kernel(256)
-        t1024 = time_bilinear_kernel(1024)
-    ach = 32 * K1_FWD_BYTES_PER_IMG / t_avg / 1e9
-    ach256 = 256 * K1_FWD_BYTES_PER_IMG / t256 / 1e9
-    ach1024 = 1024 * K1_FWD_BYTES_PER_IMG / t1024 / 1e9
-    flops_img = VGG16_FWD_GFLOP_PER_IMG * (3.0 if args.stage == 2 else 1.0) * 1e9
-    conv_tf = flops_img * B * args.steps / (ms * 1e-3) / 1e12
+    conv_tf = W['fwd_gflop'] * W['bwd_mult'] * 1e9 * B * args.steps / (ms * 1e-3) / 1e12
     line = {
-        'metric': METRIC, 'value': value, 'unit': 'img/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'metric': metric_name(args.workload), 'value': value, 'unit': 'img/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': warm, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'tf32 (fp32 storage, fp32 accumulate)', 'data': 'synthetic',
-        'config': {'workload': f'BCNN VGG-16 stage {args.stage}, 448x448, batch {B}/GPU, 200 classes, SGD momentum',
+        'config': {'workload': f'{W["model"]}, 448x448, batch {B}/GPU, 200 classes ({W["cfg"]})',
                    'global_batch': B * world, 'parallelism': f'dp{world}',
-                   'l2': 'per-step working set (7.7 GB activations) >> 126 MB L2; pool microbench rotates through buffer '
+                   'l2': 'per-step working set (GBs of activations) >> 126 MB L2; kernel microbenches rotate through buffer '
                          'sets totalling >= 640 MB (5x L2), so every launch reads cold inputs',
                    'final_loss': final_loss},
         'clocks': clocks,
         'e2e': {'value': e2e, 'unit': 'img/s', 'ms_per_step': ms_e2e / args.steps,
                 'h2d_bytes_per_step': x_host.numel() * 4 + y_host.numel() * 8, 'd2h_bytes_per_step': 8},
         'gpu_launches': launches,
-        'roofline': {'kernel': 'hk_bilinear_pool_fwd = bcnn_gram_fwd_kernel<512> (one launch: Gram + sqrt + L2 normalise), '
-                               'B=32 (the per-GPU batch of this workload), C=512, HW=196',
-                     'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
-                     'traffic': K1_DRAM_TRAFFIC_B32, 'peak_source': which, 'us_per_launch': t_avg * 1e6,
-                     'algorithmic_bytes_per_launch': 32 * K1_FWD_BYTES_PER_IMG,
-                     'note': 'B=32 moves 46 MB in ~20 us: launch/fill latency bound, and the 33.5 MB output stays in the '
-                             '126 MB L2 (ncu: 12.9 MB of DRAM traffic per launch); the streaming regime is b256/b1024',
-                     'b256': {'achieved': ach256, 'frac': ach256 / hbm_peak, 'us_per_launch': t256 * 1e6,
-                              'traffic': K1_DRAM_TRAFFIC_B256},
-                     'b1024': {'achieved': ach1024, 'frac': ach1024 / hbm_peak, 'us_per_launch': t1024 * 1e6}},
         'roofline_conv': {'bound': 'tensor', 'achieved': conv_tf, 'unit': 'TFLOP/s (tf32, whole step incl. non-conv time)',
                           'peak': tf_peak / 2, 'frac': conv_tf / (tf_peak / 2),
                           'note': 'peak = measured bf16 sustained / 2 (tf32 runs at half the bf16 rate)'},
     }
+    del tr
+    torch.cuda.empty_cache()
+    if not args.no_micro:
+        t32, t256, t1024 = time_bilinear_kernel(32), time_bilinear_kernel(256), time_bilinear_kernel(1024)
+
+        def bw(B_, t, per_img):
+            a = B_ * per_img / t / 1e9
+            return {'achieved': a, 'frac': a / hbm_peak, 'us_per_launch': t * 1e6}
+        r32 = bw(32, t32, K1_FWD_BYTES_PER_IMG)
+        line['roofline'] = {
+            'kernel': 'hk_bilinear_pool_fwd = bcnn_cluster_fwd_kernel (one launch: Gram + sqrt + L2 normalise; clusters of 4 '
+                      'CTAs, X multicast once per image), B=32 (the per-GPU batch of this workload), C=512, HW=196',
+            'bound': 'hbm', 'achieved': r32['achieved'], 'peak': hbm_peak, 'unit': 'GB/s', 'frac': r32['frac'],
+            'traffic': K1_DRAM_TRAFFIC[32], 'peak_source': which, 'us_per_launch': r32['us_per_launch'],
+            'algorithmic_bytes_per_launch': 32 * K1_FWD_BYTES_PER_IMG,
+            'b256': dict(bw(256, t256, K1_FWD_BYTES_PER_IMG), traffic=K1_DRAM_TRAFFIC[256]),
+            'b1024': bw(1024, t1024, K1_FWD_BYTES_PER_IMG)}
+    if not args.no_micro and world == 1:
+        tb32, tb256 = time_bilinear_kernel(32, bwd=True), time_bilinear_kernel(256, bwd=True)
+        line['roofline_bwd'] = {'kernel': 'hk_bilinear_pool_bwd (K1b), B=32, C=512, HW=196', 'bound': 'hbm', 'peak': hbm_peak,
+                                'unit': 'GB/s', 'algorithmic_bytes_per_launch': 32 * K1_BWD_BYTES_PER_IMG,
+                                **bw(32, tb32, K1_BWD_BYTES_PER_IMG), 'b256': bw(256, tb256, K1_BWD_BYTES_PER_IMG)}
+        tc32, tc256 = time_cbp_kernel(32), time_cbp_kernel(256)
+        line['roofline_cbp'] = {'kernel': 'hk_cbp_fwd (K2: Gram -> signed scatter into d=8192 bins -> signed sqrt + L2), B=32',
+                                'bound': 'hbm', 'peak': hbm_peak, 'unit': 'GB/s',
+                                'algorithmic_bytes_per_launch': 32 * (401408 + 4 * 8192),
+                                **bw(32, tc32, 401408 + 4 * 8192), 'b256': bw(256, tc256, 401408 + 4 * 8192)}
+        tm = time_mpncov_head(32)
+        mtf = 32 * MPNCOV_GFLOP_PER_IMG * 1e9 / tm / 1e12
+        line['roofline_mpncov'] = {'kernel': 'covpool + sqrtm(5) + triuvec, fwd+bwd (K3/K4), B=32, C=256, HW=196', 'bound': 'tensor',
+                                   'achieved': mtf, 'unit': 'TFLOP/s (algorithmic tf32 flops; executed 3x as 3xTF32)',
+                                   'peak': tf_peak / 2, 'frac': mtf / (tf_peak / 2), 'ms_per_call': tm * 1e3}
+    if not args.no_eager and world == 1 and args.workload in ('bcnn_s1', 'bcnn_s2'):
+        try:
+            line['eager_gpu'] = eager_gpu_bcnn(1 if args.workload == 'bcnn_s1' else 2, B, max(3, min(args.steps, 10)))
+        except Exception as e:          # e.g. out of memory next to a large resident workload
+            line['eager_gpu'] = {'unavailable': repr(e)[:200]}
     if not args.no_cpu_baseline:
-        threads = host_threads()
-        ips, dt = cpu_step_port(args.stage, 2, threads, 2)
-        line['cpu_baseline'] = {'value': ips, 'unit': 'img/s', 'cores': threads, 'kind': 'port',
-                                'sample': f'2 timed steps of batch 2 ({dt:.2f} s/step), torch-CPU oracle port of the '
-                                          f'reference BCNN step (fwd+CE+bwd+SGD), {threads} threads'}
+        cb = cpu_baseline(args.workload, 2)
+        cb.pop('dt')
+        line['cpu_baseline'] = cb
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -43,7 +43,15 @@ struct CfArgs {
   float* Y;          // [B][512*512]
   float* inv_norm;   // [B] or null
   int pdl;           // launched with programmatic stream serialization
+  int dbg;           // profiling only ($HK_K1_DBG): 1 skip the channel-sum reads, 2 skip the global stores, 4 skip the MMAs
+  unsigned long long* trace;   // profiling only: [grid][16] %globaltimer stamps, or null
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -161,6 +169,8 @@ bcnn_cluster_fwd_kernel(const __grid_constant__ CUtensorMap tmX, CfArgs a) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
   }
 
+  unsigned long long* tr = a.trace ? a.trace + (size_t)blockIdx.x * 16 : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = gtimer();
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer: my row block, multicast to all
     if (lane == 0) {
@@ -188,13 +198,14 @@ bcnn_cluster_fwd_kernel(const __grid_constant__ CUtensorMap tmX, CfArgs a) {
         const uint32_t ph = (kbg / CF_STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
+        if (tr && lane == 0 && kb == 0 && it < 2) tr[1 + 4 * it] = gtimer();
         const uint32_t s0 = smem_u32(stages + s * CF_STAGE_BYTES);
         const uint64_t da = desc_tmpl + ((s0 + rank * CF_SLOT) >> 4);
         const uint64_t db0 = desc_tmpl + (s0 >> 4), db1 = desc_tmpl + ((s0 + 2 * CF_SLOT) >> 4);
         const int krem = a.HW - kb * 32;
         const int ksteps = krem >= 32 ? 4 : (krem + 7) / 8;
         if (elect_one()) {
-          for (int ks = 0; ks < ksteps; ++ks) {
+          for (int ks = 0; ks < ksteps && !(a.dbg & 4); ++ks) {
             const uint32_t accum = (kb | ks) ? 1u : 0u;
             umma_tf32_ss(tmem_base, da + ks * 2, db0 + ks * 2, idesc, accum);          // columns   0..255: rows 0..255 of X
             umma_tf32_ss(tmem_base + 256, da + ks * 2, db1 + ks * 2, idesc, accum);    // columns 256..511
@@ -203,6 +214,7 @@ bcnn_cluster_fwd_kernel(const __grid_constant__ CUtensorMap tmX, CfArgs a) {
         }
         __syncwarp();
       }
+      if (tr && lane == 0 && it < 2) tr[2 + 4 * it] = gtimer();
       if (elect_one()) umma_commit(acc_full);
       __syncwarp();
     }
@@ -217,6 +229,7 @@ bcnn_cluster_fwd_kernel(const __grid_constant__ CUtensorMap tmX, CfArgs a) {
       const float inv_norm = inv_box[it & 1];
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
+      if (tr && threadIdx.x == 64 && it < 2) tr[3 + 4 * it] = gtimer();
       float* ybase = a.Y + (size_t)img * CF_C * CF_C + rank * 128 + q * 32 + lane;
 #pragma unroll 1
       for (int c = 8 * h; c < 8 * h + 8; ++c) {
@@ -224,13 +237,21 @@ bcnn_cluster_fwd_kernel(const __grid_constant__ CUtensorMap tmX, CfArgs a) {
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
         tmem_ld_wait();
         float* y = ybase + (size_t)(c * 32) * CF_C;
+        if (a.dbg & 2) {
+          float keep = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          y[(size_t)j * CF_C] = tf32_round(sqrt_approx(fmaf(v[j], a.inv_hw, a.eps)) * inv_norm);
+          for (int j = 0; j < 32; ++j) keep += tf32_round(sqrt_approx(fmaf(v[j], a.inv_hw, a.eps)) * inv_norm);
+          if (keep == 123.456f) y[0] = keep;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            y[(size_t)j * CF_C] = tf32_round(sqrt_approx(fmaf(v[j], a.inv_hw, a.eps)) * inv_norm);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
+      if (tr && threadIdx.x == 64 && it < 2) tr[4 + 4 * it] = gtimer();
     }
   } else {
     // ------------------------------------------------------------------ channel sums -> 1/||z||  (4 warps, 128 threads)
@@ -250,7 +271,7 @@ bcnn_cluster_fwd_kernel(const __grid_constant__ CUtensorMap tmX, CfArgs a) {
         for (int i = 0; i < 32; ++i) acc[i] = 0.f;
         const uint8_t* row0 = stages + s * CF_STAGE_BYTES + t * 128;
 #pragma unroll
-        for (int blk = 0; blk < CF_CLUSTER; ++blk) {
+        for (int blk = 0; blk < CF_CLUSTER && !(a.dbg & 1); ++blk) {
 #pragma unroll
           for (int lc = 0; lc < 8; ++lc) {
             const float4 v = *reinterpret_cast<const float4*>(row0 + blk * CF_SLOT + ((lc ^ (t & 7)) << 4));
@@ -290,17 +311,22 @@ bcnn_cluster_fwd_kernel(const __grid_constant__ CUtensorMap tmX, CfArgs a) {
           const float inn = 1.f / fmaxf(nrm, 1e-12f);
           inv_box[it & 1] = inn;
           mbar_arrive(&norm_ready[it & 1]);
+          if (tr && it < 2) tr[9 + it] = gtimer();
           if (rank == 0 && a.inv_norm) a.inv_norm[img] = inn;
         }
         __syncwarp();
       }
     }
   }
+  if (tr && threadIdx.x == 0) tr[11] = gtimer();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();          // no peer is still multicasting into this CTA or arriving on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
+
+static unsigned long long* g_k1_trace = nullptr;
+void set_k1_trace(void* buf) { g_k1_trace = static_cast<unsigned long long*>(buf); }
 
 // x [B,512,HW] -> y [B,512*512]; returns 0, <0 (argument) or >0 (cudaError_t); HK_ERR_UNSUPPORTED if clusters of four
 // cannot be scheduled with this much shared memory (the caller then uses the two-kernel path).
@@ -345,6 +371,8 @@ int bcnn_cluster_fwd(const CUtensorMap& tmX, float* y, float* inv_norm, int B, i
   if (pdl < 0) { const char* v = getenv("HK_K1_PDL"); pdl = v ? atoi(v) : 1; }
   CfArgs a = {};
   a.B = B; a.HW = HW; a.inv_hw = 1.f / (float)HW; a.eps = 1e-5f; a.Y = y; a.inv_norm = inv_norm; a.pdl = pdl;
+  { const char* v = getenv("HK_K1_DBG"); a.dbg = v ? atoi(v) : 0; }
+  a.trace = g_k1_trace;
   const int ncl = B < max_clusters ? B : max_clusters;
   cfg.gridDim = dim3(ncl * CF_CLUSTER);
   cfg.numAttrs = pdl ? 2 : 1;
@@ -355,3 +383,6 @@ int bcnn_cluster_fwd(const CUtensorMap& tmX, float* y, float* inv_norm, int B, i
 }
 
 }  // namespace hk
+
+/* profiling aid (not part of the ABI header): per-CTA %globaltimer stamps of the following K1 launches go to buf */
+extern "C" void hk_debug_k1_trace(void* buf) { hk::set_k1_trace(buf); }

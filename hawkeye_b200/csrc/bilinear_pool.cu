@@ -29,6 +29,8 @@
 namespace hk {
 
 int bcnn_cluster_fwd(const CUtensorMap& tmX, float* y, float* inv_norm, int B, int HW, cudaStream_t stream);   // bilinear_fwd.cu
+int bcnn_tiles_fwd(const CUtensorMap& tmX, const float* x, float* y, float* inv_norm, int B, int C, int HW,
+                   cudaStream_t stream);                                                                       // bilinear_fwd_tiles.cu
 
 __device__ __forceinline__ float fast_sqrt(float x) {
   float r;
@@ -520,11 +522,20 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
   }
   CUtensorMap tm;
   if ((r = make_x_map(&tm, x, B, C, HW))) return r;
-  static int use_cluster = -1;
-  if (use_cluster < 0) { const char* v = getenv("HK_K1_CLUSTER"); use_cluster = v ? atoi(v) : 1; }
-  if (C == 512 && use_cluster) {
+  // $HK_K1: "tiles" (default) = persistent 128x128-tile kernel, bounded-wait norm exchange (bilinear_fwd_tiles.cu);
+  //         "cluster" = 4-CTA clusters, X multicast, no exchange at all (bilinear_fwd.cu; C = 512); "two" = pre-kernel + pairs
+  static int variant = -1;
+  if (variant < 0) {
+    const char* v = getenv("HK_K1");
+    variant = (v && v[0] == 'c') ? 1 : ((v && v[0] == 't' && v[1] == 'w') ? 2 : 0);
+  }
+  if (variant == 1 && C == 512) {
     r = bcnn_cluster_fwd(tm, y, invn, B, HW, stream);
-    if (r != HK_ERR_UNSUPPORTED) return r;        // clusters of four not schedulable on this device: two-kernel path below
+    if (r != HK_ERR_UNSUPPORTED) return r;
+  }
+  if (variant != 2) {
+    r = bcnn_tiles_fwd(tm, x, y, invn, B, C, HW, stream);
+    if (r != HK_ERR_UNSUPPORTED) return r;        // more tiles per image than the slot table holds: two-kernel path
   }
   GramArgs a = {};
   a.C = C; a.HW = HW; a.nblk = C / 128;

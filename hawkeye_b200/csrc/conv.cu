@@ -32,13 +32,14 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, float* __restri
   }
 }
 // dWp [9][Cout][Cin] -> dW [Cout][Cin][3][3]
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dWp, float* __restrict__ dW, int Cout, int Cin) {
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dWp, float* __restrict__ dW, int Cout, int Cin, int accumulate) {
   const size_t n = (size_t)Cout * Cin * 9;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int t = i % 9;
     const int ci = (i / 9) % Cin;
     const int co = i / ((size_t)9 * Cin);
-    dW[i] = dWp[((size_t)t * Cout + co) * Cin + ci];
+    const float v = dWp[((size_t)t * Cout + co) * Cin + ci];
+    dW[i] = accumulate ? dW[i] + v : v;
   }
 }
 
@@ -709,8 +710,8 @@ static int conv3x3_wgrad_1x(const float* x, const float* dy, float* dwp, float* 
                             cudaStream_t stream, bool zero_dw, bool zero_db);
 
 int conv3x3_wgrad(const float* x, const float* dy, float* dwp, float* db, int N, int H, int W, int Cin, int Cout,
-                  cudaStream_t stream) {
-  if (!precise()) return conv3x3_wgrad_1x(x, dy, dwp, db, N, H, W, Cin, Cout, stream, true, true);
+                  cudaStream_t stream, bool zero_db = true) {
+  if (!precise()) return conv3x3_wgrad_1x(x, dy, dwp, db, N, H, W, Cin, Cout, stream, true, zero_db);
   // 3xTF32: dW = dYh^T Xh + dYh^T Xl + dYl^T Xh accumulated by the kernel's own atomics; db = sum(dYh) + sum(dYl)
   HK_REQUIRE(x && dy && dwp, HK_ERR_ARG, "conv3x3_wgrad: null pointer");
   const size_t nx = (size_t)N * H * W * Cin, ny = (size_t)N * H * W * Cout;
@@ -720,7 +721,7 @@ int conv3x3_wgrad(const float* x, const float* dy, float* dwp, float* db, int N,
   int r;
   if ((r = tf32_split(x, xh, xl, nx, stream))) return r;
   if ((r = tf32_split(dy, yh, yl, ny, stream))) return r;
-  if ((r = conv3x3_wgrad_1x(xh, yh, dwp, db, N, H, W, Cin, Cout, stream, true, true))) return r;
+  if ((r = conv3x3_wgrad_1x(xh, yh, dwp, db, N, H, W, Cin, Cout, stream, true, zero_db))) return r;
   if ((r = conv3x3_wgrad_1x(xl, yh, dwp, nullptr, N, H, W, Cin, Cout, stream, false, false))) return r;
   return conv3x3_wgrad_1x(xh, yl, dwp, db, N, H, W, Cin, Cout, stream, false, false);
 }
@@ -829,14 +830,14 @@ __global__ void pack_first_weights_kernel(const float* __restrict__ w, const flo
 }
 // dw[co][r] = sum_s part[s][co][r] (r<27), db[co] = sum_s part[s][co][27]
 __global__ void first_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw,
-                                          float* __restrict__ db, int Cout, int S) {
+                                          float* __restrict__ db, int Cout, int S, int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Cout * 28) return;
   const int co = i / 28, r = i % 28;
   float s = 0.f;
   for (int k = 0; k < S; ++k) s += part[((size_t)k * Cout + co) * 32 + r];
-  if (r < 27) dw[co * 27 + r] = s;
-  else if (db) db[co] = s;
+  if (r < 27) dw[co * 27 + r] = accumulate ? dw[co * 27 + r] + s : s;
+  else if (db) db[co] = accumulate ? db[co] + s : s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -894,6 +895,70 @@ __global__ void maxpool2x2_bwd_kernel(const float* __restrict__ x, const float* 
     dx[b01] = arg == 1 ? gm : 0.f;
     dx[b10] = arg == 2 ? gm : 0.f;
     dx[b11] = arg == 3 ? gm : 0.f;
+  }
+}
+
+// Training variants: the forward also records, per pooled element, ONE byte — bits 0-1 = window position of the first
+// maximum in scan order (PyTorch routing), bit 2 = (max > 0), i.e. the mask of the ReLU that precedes the pool — and the
+// backward routes dy from that byte alone: it no longer re-reads the four pre-pool activations (1/16 of the bytes).
+__global__ void maxpool2x2_fwd_idx_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned char* __restrict__ code,
+                                          int N, int H, int W, int C, int out_nchw) {
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const size_t total = (size_t)N * Ho * Wo * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = i % C4;
+    size_t p = i / C4;
+    const int wo = p % Wo; p /= Wo;
+    const int ho = p % Ho;
+    const int n = p / Ho;
+    const float4* base = reinterpret_cast<const float4*>(x + (((size_t)n * H + 2 * ho) * W + 2 * wo) * C) + c4;
+    const float4 v0 = base[0], v1 = base[C4], v2 = base[(size_t)W * C4], v3 = base[(size_t)W * C4 + C4];
+    float4 m = v0;
+    uchar4 a = make_uchar4(0, 0, 0, 0);
+#define HK_POOL_STEP(V, K)                     \
+    if (V.x > m.x) { m.x = V.x; a.x = K; }     \
+    if (V.y > m.y) { m.y = V.y; a.y = K; }     \
+    if (V.z > m.z) { m.z = V.z; a.z = K; }     \
+    if (V.w > m.w) { m.w = V.w; a.w = K; }
+    HK_POOL_STEP(v1, 1) HK_POOL_STEP(v2, 2) HK_POOL_STEP(v3, 3)
+#undef HK_POOL_STEP
+    a.x |= m.x > 0.f ? 4 : 0; a.y |= m.y > 0.f ? 4 : 0; a.z |= m.z > 0.f ? 4 : 0; a.w |= m.w > 0.f ? 4 : 0;
+    reinterpret_cast<uchar4*>(code)[i] = a;
+    if (!out_nchw) {
+      reinterpret_cast<float4*>(y + (((size_t)n * Ho + ho) * Wo + wo) * C)[c4] = m;
+    } else {
+      const size_t hw = (size_t)Ho * Wo, o = ((size_t)n * C + c4 * 4) * hw + (size_t)ho * Wo + wo;
+      y[o] = m.x; y[o + hw] = m.y; y[o + 2 * hw] = m.z; y[o + 3 * hw] = m.w;
+    }
+  }
+}
+__global__ void maxpool2x2_bwd_idx_kernel(const unsigned char* __restrict__ code, const float* __restrict__ dy,
+                                          float* __restrict__ dx, int N, int H, int W, int C, int dy_nchw) {
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const size_t total = (size_t)N * Ho * Wo * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = i % C4;
+    size_t p = i / C4;
+    const int wo = p % Wo; p /= Wo;
+    const int ho = p % Ho;
+    const int n = p / Ho;
+    const uchar4 a = reinterpret_cast<const uchar4*>(code)[i];
+    float4 g;
+    if (!dy_nchw) {
+      g = reinterpret_cast<const float4*>(dy)[i];
+    } else {
+      const size_t hw = (size_t)Ho * Wo, o = ((size_t)n * C + c4 * 4) * hw + (size_t)ho * Wo + wo;
+      g = make_float4(dy[o], dy[o + hw], dy[o + 2 * hw], dy[o + 3 * hw]);
+    }
+    g.x = (a.x & 4) ? g.x : 0.f; g.y = (a.y & 4) ? g.y : 0.f; g.z = (a.z & 4) ? g.z : 0.f; g.w = (a.w & 4) ? g.w : 0.f;
+    float4* base = reinterpret_cast<float4*>(dx + (((size_t)n * H + 2 * ho) * W + 2 * wo) * C) + c4;
+#define HK_POOL_OUT(K) make_float4((a.x & 3) == K ? g.x : 0.f, (a.y & 3) == K ? g.y : 0.f, (a.z & 3) == K ? g.z : 0.f, \
+                                   (a.w & 3) == K ? g.w : 0.f)
+    base[0] = HK_POOL_OUT(0);
+    base[C4] = HK_POOL_OUT(1);
+    base[(size_t)W * C4] = HK_POOL_OUT(2);
+    base[(size_t)W * C4 + C4] = HK_POOL_OUT(3);
+#undef HK_POOL_OUT
   }
 }
 
@@ -961,17 +1026,23 @@ int hk_conv3x3_dgrad(const float* dy, const float* w_dgrad_packed, const float* 
 
 size_t hk_conv3x3_wgrad_workspace_bytes(int Cin, int Cout) { return (size_t)9 * Cin * Cout * sizeof(float); }
 
-int hk_conv3x3_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int H, int W, int Cin, int Cout,
-                     void* workspace, size_t workspace_bytes, void* stream_) {
+int hk_conv3x3_wgrad_acc(const float* x, const float* dy, float* dw, float* db, int N, int H, int W, int Cin, int Cout,
+                         void* workspace, size_t workspace_bytes, int accumulate, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   HK_REQUIRE(workspace && workspace_bytes >= hk_conv3x3_wgrad_workspace_bytes(Cin, Cout), HK_ERR_WORKSPACE,
              "hk_conv3x3_wgrad: workspace too small");
+  HK_REQUIRE(dw, HK_ERR_ARG, "hk_conv3x3_wgrad: null dw");
   float* dwp = static_cast<float*>(workspace);
-  int r = conv3x3_wgrad(x, dy, dwp, db, N, H, W, Cin, Cout, stream);
+  int r = conv3x3_wgrad(x, dy, dwp, db, N, H, W, Cin, Cout, stream, /*zero_db=*/!accumulate);
   if (r) return r;
-  unpack_wgrad_kernel<<<grid_for((size_t)Cout * Cin * 9, 256), 256, 0, stream>>>(dwp, dw, Cout, Cin);
+  unpack_wgrad_kernel<<<grid_for((size_t)Cout * Cin * 9, 256), 256, 0, stream>>>(dwp, dw, Cout, Cin, accumulate ? 1 : 0);
   HK_LAUNCH_CHECK("unpack_wgrad_kernel");
   return 0;
+}
+
+int hk_conv3x3_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int H, int W, int Cin, int Cout,
+                     void* workspace, size_t workspace_bytes, void* stream_) {
+  return hk_conv3x3_wgrad_acc(x, dy, dw, db, N, H, W, Cin, Cout, workspace, workspace_bytes, 0, stream_);
 }
 
 size_t hk_conv3x3_first_fwd_workspace_bytes(int N, int H, int W, int Cout) {
@@ -1013,8 +1084,14 @@ size_t hk_conv3x3_first_wgrad_workspace_bytes(int N, int H, int W, int Cout) {
 
 /* dw [Cout,3,3,3], db [Cout] of the input layer from X27 (written by hk_conv3x3_first_fwd) and dy (ReLU-masked):
  * split-K batched MN-major tcgen05 GEMM  partial[s] = dY_s^T . X27_s ; column 27 of the result is the bias grad. */
+int hk_conv3x3_first_wgrad_acc(const float* x27, const float* dy_nhwc, float* dw, float* db, int N, int H, int W, int Cout,
+                               void* workspace, size_t workspace_bytes, int accumulate, void* stream_);
 int hk_conv3x3_first_wgrad(const float* x27, const float* dy_nhwc, float* dw, float* db, int N, int H, int W,
                            int Cout, void* workspace, size_t workspace_bytes, void* stream_) {
+  return hk_conv3x3_first_wgrad_acc(x27, dy_nhwc, dw, db, N, H, W, Cout, workspace, workspace_bytes, 0, stream_);
+}
+int hk_conv3x3_first_wgrad_acc(const float* x27, const float* dy_nhwc, float* dw, float* db, int N, int H, int W, int Cout,
+                               void* workspace, size_t workspace_bytes, int accumulate, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   HK_REQUIRE(x27 && dy_nhwc && dw, HK_ERR_ARG, "hk_conv3x3_first_wgrad: null pointer");
   HK_REQUIRE(Cout % 4 == 0 && Cout <= 128, HK_ERR_UNSUPPORTED, "hk_conv3x3_first_wgrad: Cout=%d unsupported", Cout);
@@ -1027,7 +1104,7 @@ int hk_conv3x3_first_wgrad(const float* x27, const float* dy_nhwc, float* dw, fl
   int r = hk_gemm_tf32(dy_nhwc, 1, Cout, Kc * Cout, x27, 1, 32, Kc * 32, part, 32, (long long)Cout * 32, 0, Cout, 32,
                        (int)Kc, S, 1.f, nullptr, 0.f, nullptr, 0, 0, 0.f, nullptr, 0, stream_);
   if (r) return r;
-  first_wgrad_reduce_kernel<<<(Cout * 28 + 127) / 128, 128, 0, stream>>>(part, dw, db, Cout, S);
+  first_wgrad_reduce_kernel<<<(Cout * 28 + 127) / 128, 128, 0, stream>>>(part, dw, db, Cout, S, accumulate ? 1 : 0);
   HK_LAUNCH_CHECK("first_wgrad_reduce_kernel");
   return 0;
 }
@@ -1048,6 +1125,26 @@ int hk_maxpool2x2_bwd(const float* x_nhwc, const float* dy, float* dx_nhwc, int 
   const size_t total = (size_t)N * (H / 2) * (W / 2) * C;
   maxpool2x2_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x_nhwc, dy, dx_nhwc, N, H, W, C, dy_nchw);
   HK_LAUNCH_CHECK("maxpool2x2_bwd_kernel");
+  return 0;
+}
+
+int hk_maxpool2x2_fwd_idx(const float* x_nhwc, float* y, unsigned char* code, int N, int H, int W, int C, int out_nchw,
+                          void* stream) {
+  HK_REQUIRE(x_nhwc && y && code, HK_ERR_ARG, "hk_maxpool2x2_fwd_idx: null pointer");
+  HK_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, HK_ERR_UNSUPPORTED, "hk_maxpool2x2_fwd_idx: C%%4, even H/W required");
+  const size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 4);
+  maxpool2x2_fwd_idx_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x_nhwc, y, code, N, H, W, C, out_nchw);
+  HK_LAUNCH_CHECK("maxpool2x2_fwd_idx_kernel");
+  return 0;
+}
+
+int hk_maxpool2x2_bwd_idx(const unsigned char* code, const float* dy, float* dx_nhwc, int N, int H, int W, int C,
+                          int dy_nchw, void* stream) {
+  HK_REQUIRE(code && dy && dx_nhwc, HK_ERR_ARG, "hk_maxpool2x2_bwd_idx: null pointer");
+  HK_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, HK_ERR_UNSUPPORTED, "hk_maxpool2x2_bwd_idx: C%%4, even H/W required");
+  const size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 4);
+  maxpool2x2_bwd_idx_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(code, dy, dx_nhwc, N, H, W, C, dy_nchw);
+  HK_LAUNCH_CHECK("maxpool2x2_bwd_idx_kernel");
   return 0;
 }
 

@@ -29,9 +29,12 @@ class BCNN(nn.Module):
                 p.requires_grad = False
         self.backbone.train_backbone = self.stage != 1
 
-    def forward(self, x):
+    def features(self, x):
         x = self.backbone(x)
-        if self.stage == 1:
-            x = x.detach()
-        x = self.bilinear_pooling(x)
-        return ops.linear(x, self.classifier.weight, self.classifier.bias)
+        return x.detach() if self.stage == 1 else x                      # BCNN.py:51-52
+
+    def head(self, feat):
+        return ops.linear(self.bilinear_pooling(feat), self.classifier.weight, self.classifier.bias)
+
+    def forward(self, x):
+        return self.head(self.features(x))

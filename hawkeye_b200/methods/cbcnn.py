@@ -57,9 +57,12 @@ class CBCNN(nn.Module):
         self.classifier.apply(initialize_weights)
         self.backbone.train_backbone = config.stage != 1
 
-    def forward(self, x):
+    def features(self, x):
         x = self.backbone(x)
-        if self.config.stage == 1:                                              # CBCNN.py:31-32
-            x = x.detach()
-        x = self.bilinear_pooling(x)
-        return ops.linear(x, self.classifier.weight, self.classifier.bias)
+        return x.detach() if self.config.stage == 1 else x                      # CBCNN.py:31-32
+
+    def head(self, feat):
+        return ops.linear(self.bilinear_pooling(feat), self.classifier.weight, self.classifier.bias)
+
+    def forward(self, x):
+        return self.head(self.features(x))

@@ -16,6 +16,16 @@ VGG16_D = (64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 5
 # so that a CPU oracle can be evaluated on the same branch of the piecewise-smooth function (oracle.hop_oracle.MaskTape).
 CAPTURE = None
 
+# Backbone weight/bias gradients are accumulated by the wgrad kernels directly into an existing ``param.grad`` (see
+# VGGFeaturesFn.backward).  Set to False to make every backward return fresh gradient tensors to autograd instead.
+ACCUMULATE_INTO_GRAD = True
+
+
+def _grad_ready(p):
+    g = getattr(p, 'grad', None)
+    return (g is not None and p.requires_grad and g.is_cuda and g.dtype == torch.float32 and g.is_contiguous()
+            and g.shape == p.shape and not p._backward_hooks and not getattr(p, '_post_accumulate_grad_hooks', None))
+
 
 def _check_cuda(*ts):
     for t in ts:
@@ -204,15 +214,21 @@ class VGGFeaturesFn(Function):
                 last = idx == len(plan) - 1
                 Ho, Wo = H // 2, W // 2
                 out = torch.empty((N, C, Ho, Wo) if last else (N, Ho, Wo, C), device=dev, dtype=torch.float32)
-                _lib.call('hk_maxpool2x2_fwd', cur, out, N, H, W, C, 1 if last else 0, s)
+                code = None
+                if save:     # one byte per pooled element (arg-max position + ReLU mask) is all the backward needs
+                    code = torch.empty(N, Ho, Wo, C, device=dev, dtype=torch.uint8)
+                    _lib.call('hk_maxpool2x2_fwd_idx', cur, out, code, N, H, W, C, 1 if last else 0, s)
+                else:
+                    _lib.call('hk_maxpool2x2_fwd', cur, out, N, H, W, C, 1 if last else 0, s)
                 if CAPTURE is not None:
                     CAPTURE.append(('pool2', cur))
-                records.append(dict(kind='pool', inp=cur, H=H, W=W, C=C, last=last))
+                records.append(dict(kind='pool', code=code, H=H, W=W, C=C, last=last))
                 cur, H, W = out, Ho, Wo
         if save:
             ctx.records = records
             ctx.x = x
             ctx.N = N
+            ctx.params = params      # the nn.Parameters themselves: backward accumulates into their .grad when it can
         else:
             ctx.records = None
         ctx.nparams = len(params)
@@ -230,28 +246,40 @@ class VGGFeaturesFn(Function):
         li = ctx.nparams // 2
         for rec in reversed(ctx.records):
             if rec['kind'] == 'pool':
-                dx = torch.empty_like(rec['inp'])
-                _lib.call('hk_maxpool2x2_bwd', rec['inp'], g, dx, N, rec['H'], rec['W'], rec['C'],
+                dx = torch.empty(N, rec['H'], rec['W'], rec['C'], device=dev, dtype=torch.float32)
+                _lib.call('hk_maxpool2x2_bwd_idx', rec['code'], g, dx, N, rec['H'], rec['W'], rec['C'],
                           1 if rec['last'] else 0, s)
+                rec['code'] = None
                 g = dx
                 continue
             li -= 1
             H, W, cin, cout = rec['H'], rec['W'], rec['cin'], rec['cout']
-            dw = torch.empty(cout, cin, 3, 3, device=dev, dtype=torch.float32)
-            db = torch.empty(cout, device=dev, dtype=torch.float32)
+            # Accumulate straight into the parameters' .grad buffers when they exist (the Trainer keeps them as views of
+            # one flat buffer): same semantics as autograd's own accumulation, without the temporaries and the 26 `add`
+            # launches.  Otherwise (first backward, .grad is None) return fresh tensors and let autograd install them.
+            pw, pb = ctx.params[2 * li], ctx.params[2 * li + 1]
+            direct = ACCUMULATE_INTO_GRAD and _grad_ready(pw) and _grad_ready(pb)
+            if direct:
+                dw, db, acc = pw.grad, pb.grad, 1
+            else:
+                dw = torch.empty(cout, cin, 3, 3, device=dev, dtype=torch.float32)
+                db = torch.empty(cout, device=dev, dtype=torch.float32)
+                acc = 0
             if rec['kind'] == 'conv0':
                 ws = _ws(_lib.query('hk_conv3x3_first_wgrad_workspace_bytes', N, H, W, cout), dev)
-                _lib.call('hk_conv3x3_first_wgrad', rec['x27'], g, dw, db, N, H, W, cout, ws, ws.numel(), s)
+                _lib.call('hk_conv3x3_first_wgrad_acc', rec['x27'], g, dw, db, N, H, W, cout, ws, ws.numel(), acc, s)
             else:
                 ws = _ws(_lib.query('hk_conv3x3_wgrad_workspace_bytes', cin, cout), dev)
-                _lib.call('hk_conv3x3_wgrad', rec['inp'], g, dw, db, N, H, W, cin, cout, ws, ws.numel(), s)
+                _lib.call('hk_conv3x3_wgrad_acc', rec['inp'], g, dw, db, N, H, W, cin, cout, ws, ws.numel(), acc, s)
                 dx = torch.empty_like(rec['inp'])
                 mask = rec['inp'] if rec['inp_is_relu'] else None
                 _lib.call('hk_conv3x3_dgrad', g, rec['wd'], mask, dx, N, H, W, cin, cout, s)
                 g = dx
-            grads[2 * li], grads[2 * li + 1] = dw, db
+            if not direct:
+                grads[2 * li], grads[2 * li + 1] = dw, db
             rec['out'] = None
         ctx.records = None
+        ctx.params = None
         return (None, None, None) + tuple(grads)
 
 

@@ -105,6 +105,9 @@ int hk_conv3x3_dgrad(const float* dy_nhwc, const float* w_dgrad_packed, const fl
 size_t hk_conv3x3_wgrad_workspace_bytes(int Cin, int Cout);
 int hk_conv3x3_wgrad(const float* x_nhwc, const float* dy_nhwc, float* dw, float* db, int N, int H, int W, int Cin,
                      int Cout, void* workspace, size_t workspace_bytes, void* stream);
+/* accumulate != 0: dw += ..., db += ... (gradient accumulation straight into a parameter's .grad buffer, no temporaries) */
+int hk_conv3x3_wgrad_acc(const float* x_nhwc, const float* dy_nhwc, float* dw, float* db, int N, int H, int W, int Cin,
+                         int Cout, void* workspace, size_t workspace_bytes, int accumulate, void* stream);
 /* first layer (Cin=3, vgg.py:61): NCHW image in, NHWC out, bias+ReLU fused.  The 3x3x3 patches are materialised once
  * as X27 [N*H*W][32] (start of the fwd workspace) and reused by the weight/bias gradient. */
 size_t hk_conv3x3_first_fwd_workspace_bytes(int N, int H, int W, int Cout);
@@ -113,11 +116,19 @@ int hk_conv3x3_first_fwd(const float* x_nchw, const float* w, const float* bias,
 size_t hk_conv3x3_first_wgrad_workspace_bytes(int N, int H, int W, int Cout);
 int hk_conv3x3_first_wgrad(const float* x27, const float* dy_nhwc, float* dw, float* db, int N, int H, int W,
                            int Cout, void* workspace, size_t workspace_bytes, void* stream);
+int hk_conv3x3_first_wgrad_acc(const float* x27, const float* dy_nhwc, float* dw, float* db, int N, int H, int W,
+                               int Cout, void* workspace, size_t workspace_bytes, int accumulate, void* stream);
 /* MaxPool2d(2,2) on NHWC; out_nchw=1 writes the pooled map as NCHW (input of the pooling heads).
  * bwd routes dy to the first max (PyTorch semantics) and multiplies by (x>0), i.e. also applies the ReLU backward. */
 int hk_maxpool2x2_fwd(const float* x_nhwc, float* y, int N, int H, int W, int C, int out_nchw, void* stream);
 int hk_maxpool2x2_bwd(const float* x_nhwc, const float* dy, float* dx_nhwc, int N, int H, int W, int C, int dy_nchw,
                       void* stream);
+/* training variants: fwd also records one byte per pooled element (bits 0-1 arg-max window position, bit 2 = max > 0);
+ * bwd routes dy from that byte alone instead of re-reading the four pre-pool activations */
+int hk_maxpool2x2_fwd_idx(const float* x_nhwc, float* y, unsigned char* code, int N, int H, int W, int C, int out_nchw,
+                          void* stream);
+int hk_maxpool2x2_bwd_idx(const unsigned char* code, const float* dy, float* dx_nhwc, int N, int H, int W, int C,
+                          int dy_nchw, void* stream);
 int hk_relu_mask_inplace(float* dy, const float* act, size_t n, void* stream);
 
 /* ---- ResNet-50 v1.5 trunk support (model/backbone/resnet.py:89-252); activations NHWC [P = N*H*W, C] -----------------
@@ -151,6 +162,19 @@ int hk_nchw_to_nhwc(const float* x, float* y, int N, int HW, int C, void* stream
 size_t hk_matconv_wgrad_workspace_bytes(long long P, int K, int Cout);
 int hk_matconv_wgrad(const float* x, const float* dy, float* dw, long long P, int K, int Cout, void* workspace,
                      size_t workspace_bytes, void* stream);
+
+/* ---- channel interaction: model/methods/CIN.py:24-60, ChannelInteractionModule ---------------------
+ * The Gram (:31), W.X (:34,:55), the 3x3 conv (:36,:57) and fc (:47-48) use hk_gemm_tf32 / hk_conv3x3_* / hk_linear_*; these are
+ * the pieces in between: W_SCI = softmax(-G) row-wise (:32) and its backward; W_CCI = |W_SCI - weight_b * W_SCI[(b+B/2)%B]|
+ * (:50-53; `per` = C*C elements per sample, B even) and its backward (d_sci, d_weight [B]); AdaptiveAvgPool1d(1) (:71) as a
+ * row mean over the first `cols` of `ld` entries. */
+int hk_softmax_neg_rows_fwd(const float* g, float* w, long long rows, int cols, void* stream);
+int hk_softmax_neg_rows_bwd(const float* w, const float* dw, float* dg, long long rows, int cols, void* stream);
+int hk_cci_weight_fwd(const float* w_sci, const float* weight, float* w_cci, int B, long long per, void* stream);
+int hk_cci_weight_bwd(const float* w_sci, const float* weight, const float* d_cci, float* d_sci, float* d_weight, int B,
+                      long long per, void* stream);
+int hk_row_mean_fwd(const float* x, float* y, long long rows, int cols, int ld, void* stream);
+int hk_row_mean_bwd(const float* dy, float* dx, long long rows, int cols, int ld, void* stream);
 
 /* ---- classifier nn.Linear (BCNN.py:42, CBCNN.py:26, MPNCOV.py:31) as skinny tcgen05 GEMMs ------------------- */
 size_t hk_linear_fwd_workspace_bytes(int B, int F, int N);

@@ -64,3 +64,30 @@ def test_full_batch_properties():
     from hawkeye_b200._lib import HawkeyeLibError
     with pytest.raises(HawkeyeLibError):
         ops.bilinear_pool(torch.rand(1, 100, 4, 4, device='cuda'))
+
+
+@pytest.mark.parametrize('env', [{'HK_K1_POLL_LIMIT': '0'}, {'HK_K1': 'cluster'}, {'HK_K1': 'two'}])
+def test_k1_variants_and_bounded_wait(env):
+    """hk_bilinear_pool_fwd must be correct on every route: with the cross-CTA norm exchange of the tile kernel never
+    succeeding (HK_K1_POLL_LIMIT=0: each CTA computes the norm itself — the path taken when peers are not co-resident),
+    on the 4-CTA cluster kernel, and on the two-kernel path.  The knobs are read once per process => subprocesses."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, 'tests'); sys.path.insert(0, '.')\n"
+        "import torch, detgen\n"
+        "from conftest import rel_l2\n"
+        "from oracle import hop_oracle as O\n"
+        "from hawkeye_b200 import ops\n"
+        "for (B, H, W) in ((3, 14, 14), (37, 14, 14), (2, 2, 2), (150, 4, 4)):\n"
+        "    x = torch.relu(detgen.det_uniform((B, 512, H, W), 5) - 0.3)\n"
+        "    y = ops.bilinear_pool(x.cuda()); torch.cuda.synchronize()\n"
+        "    ref = O.bilinear_pool_fwd(x.double())\n"
+        "    worst = max(rel_l2(y[b].cpu(), ref[b]) for b in range(B))\n"
+        "    print(B, H, W, worst); assert worst < 1e-3, worst\n"
+        "print('VARIANT_OK')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, '-c', code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True,
+                       timeout=600)
+    assert p.returncode == 0 and 'VARIANT_OK' in p.stdout, (p.stdout[-1500:], p.stderr[-1500:])

@@ -6,7 +6,7 @@ Two complementary checks (tests/matched.py explains why a plain comparison canno
     plumbing bug is O(1)).  Precise mode (hk_set_precise(1), 3xTF32 on the same kernels): <= 2e-4.
   * reference fixtures: precise mode against logits / loss / gradients of the UNMODIFIED fp32 reference
     (tests/golden/reference_448.npz, made by tests/golden/make_golden_448.py): logits, loss and the head gradients at
-    1e-3; backbone gradients at 1e-3 + 3u, where u (stored in the fixture) is how far the reference's own fp32 gradient is
+    1e-3; backbone gradients at 1e-3 + 6u, where u (stored in the fixture) is how far the reference's own fp32 gradient is
     from an exact fp64 evaluation — its own rounding flips ReLU / pool decisions, up to 4e-3 at conv1_1.
 The 64x64 input (a 2x2 feature map, HW = 4 << C) is a badly conditioned bilinear backward — a 8e-4 forward difference
 becomes 6e-3 in d(features) — so that size is asserted in precise mode only.
@@ -146,7 +146,10 @@ def _check_fixture(tag, ref448, logits, loss, grads, tol=1e-3):
         name = key[len(tag) + 3:]
         pname = name[:-len('_slice')] if name.endswith('_slice') else name
         err = rel_l2(_slice_like(grads[pname], name, ref448[key]), ref448[key])
-        bound = tol + 3 * float(ref448[f'{tag}_u_{name}'])      # u: the reference's own distance from an exact evaluation
+        # u: the reference's own distance from an exact evaluation (branch flips caused by ITS fp32 rounding, ~1e-6 forward
+        # noise).  Flip-induced error grows like sqrt(forward noise); the 3xTF32 forward carries ~2e-5 (operand split plus the
+        # tensor core's truncating fp32 accumulation), i.e. up to sqrt(20) ~ 4.5 u: bound = 1e-3 + 6 u.
+        bound = tol + 6 * float(ref448[f'{tag}_u_{name}'])
         errs[name] = (err, bound)
         if not err < bound:
             bad[name] = (err, bound)
