@@ -503,8 +503,8 @@ def main():
             return {'achieved': a, 'frac': a / hbm_peak, 'us_per_launch': t * 1e6}
         r32 = bw(32, t32, K1_FWD_BYTES_PER_IMG)
         line['roofline'] = {
-            'kernel': 'hk_bilinear_pool_fwd = bcnn_cluster_fwd_kernel (one launch: Gram + sqrt + L2 normalise; clusters of 4 '
-                      'CTAs, X multicast once per image), B=32 (the per-GPU batch of this workload), C=512, HW=196',
+            'kernel': 'hk_bilinear_pool_fwd = bcnn_gram_fwd_kernel<512> (one launch: Gram + sqrt + L2 normalise; persistent '
+                      '128x128 tiles, bounded-wait norm exchange), B=32 (the per-GPU batch of this workload), C=512, HW=196',
             'bound': 'hbm', 'achieved': r32['achieved'], 'peak': hbm_peak, 'unit': 'GB/s', 'frac': r32['frac'],
             'traffic': K1_DRAM_TRAFFIC[32], 'peak_source': which, 'us_per_launch': r32['us_per_launch'],
             'algorithmic_bytes_per_launch': 32 * K1_FWD_BYTES_PER_IMG,

@@ -330,7 +330,7 @@ void set_k1_trace(void* buf) { g_k1_trace = static_cast<unsigned long long*>(buf
 
 // x [B,512,HW] -> y [B,512*512]; returns 0, <0 (argument) or >0 (cudaError_t); HK_ERR_UNSUPPORTED if clusters of four
 // cannot be scheduled with this much shared memory (the caller then uses the two-kernel path).
-int bcnn_cluster_fwd(const CUtensorMap& tmX, float* y, float* inv_norm, int B, int HW, cudaStream_t stream) {
+int bcnn_cluster_fwd(const CUtensorMap& tmX, float* y, float* inv_norm, int B, int HW, float inv_hw, cudaStream_t stream) {
   static int max_clusters = -1;
   static bool attr_set = false;
   cudaError_t e;
@@ -370,7 +370,7 @@ int bcnn_cluster_fwd(const CUtensorMap& tmX, float* y, float* inv_norm, int B, i
   static int pdl = -1;
   if (pdl < 0) { const char* v = getenv("HK_K1_PDL"); pdl = v ? atoi(v) : 1; }
   CfArgs a = {};
-  a.B = B; a.HW = HW; a.inv_hw = 1.f / (float)HW; a.eps = 1e-5f; a.Y = y; a.inv_norm = inv_norm; a.pdl = pdl;
+  a.B = B; a.HW = HW; a.inv_hw = inv_hw; a.eps = 1e-5f; a.Y = y; a.inv_norm = inv_norm; a.pdl = pdl;
   { const char* v = getenv("HK_K1_DBG"); a.dbg = v ? atoi(v) : 0; }
   a.trace = g_k1_trace;
   const int ncl = B < max_clusters ? B : max_clusters;

@@ -468,7 +468,7 @@ static int tiles_env(const char* name, int dflt) {
 // x [B,C,HW] -> y [B,C*C] (C % 128 == 0, C/128 tiles-per-image (nblk(nblk+1)/2) <= GF_SLOTS); inv_norm [B] receives 1/||z||.
 // Returns HK_ERR_UNSUPPORTED when C has more tiles per image than the slot table holds (caller: two-kernel path).
 int bcnn_tiles_fwd(const CUtensorMap& tmX_unused, const float* x, float* y, float* inv_norm, int B, int C, int HW,
-                   cudaStream_t stream) {
+                   float inv_hw, cudaStream_t stream) {
   (void)tmX_unused;
   const int nblk = C / 128, ipi = nblk * (nblk + 1) / 2;
   if (ipi > GF_SLOTS) return set_error(HK_ERR_UNSUPPORTED, "bcnn_tiles_fwd: C=%d has more than %d tiles per image", C, GF_SLOTS);
@@ -490,7 +490,7 @@ int bcnn_tiles_fwd(const CUtensorMap& tmX_unused, const float* x, float* y, floa
     dbg = tiles_env("HK_K1_DBG", 0);
   }
   GfArgs g = {};
-  g.C = C; g.HW = HW; g.nblk = nblk; g.inv_hw = 1.f / (float)HW; g.eps = 1e-5f; g.store_mode = 1; g.x_hint = 1;
+  g.C = C; g.HW = HW; g.nblk = nblk; g.inv_hw = inv_hw; g.eps = 1e-5f; g.store_mode = 1; g.x_hint = 1;
   g.dbg = dbg; g.trace = g_tiles_trace; g.stages = stages; g.pdl = pdl; g.poll_limit = poll;
   int r;
   for (int b0 = 0; b0 < B; b0 += GRAM_CNT_MAXB) {

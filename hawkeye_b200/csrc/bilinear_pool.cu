@@ -28,8 +28,8 @@
 
 namespace hk {
 
-int bcnn_cluster_fwd(const CUtensorMap& tmX, float* y, float* inv_norm, int B, int HW, cudaStream_t stream);   // bilinear_fwd.cu
-int bcnn_tiles_fwd(const CUtensorMap& tmX, const float* x, float* y, float* inv_norm, int B, int C, int HW,
+int bcnn_cluster_fwd(const CUtensorMap& tmX, float* y, float* inv_norm, int B, int HW, float inv_hw, cudaStream_t stream);   // bilinear_fwd.cu
+int bcnn_tiles_fwd(const CUtensorMap& tmX, const float* x, float* y, float* inv_norm, int B, int C, int HW, float inv_hw,
                    cudaStream_t stream);                                                                       // bilinear_fwd_tiles.cu
 
 __device__ __forceinline__ float fast_sqrt(float x) {
@@ -437,8 +437,37 @@ static int check_gram_shape(const char* op, const float* X, int B, int C, int HW
   HK_REQUIRE(X, HK_ERR_ARG, "%s: null input", op);
   HK_REQUIRE(B > 0 && B <= 65535 && C > 0 && HW > 0, HK_ERR_ARG, "%s: bad shape B=%d C=%d HW=%d", op, B, C, HW);
   HK_REQUIRE(C % 128 == 0, HK_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of 128", op, C);
-  HK_REQUIRE(HW % 4 == 0, HK_ERR_UNSUPPORTED, "%s: H*W=%d must be a multiple of 4 (16-byte TMA row pitch)", op, HW);
   HK_REQUIRE(aligned16(X), HK_ERR_ALIGN, "%s: input not 16-byte aligned", op);
+  return 0;
+}
+
+// [rows][HW] -> [rows][HWp] zero-padded (TMA needs a 16-byte row pitch: H*W = 49 of a 224x224 input becomes 52); zero
+// columns change neither the Gram nor the channel sums, and every normalisation keeps using the true H*W
+__global__ void pad_cols_kernel(const float* __restrict__ x, float* __restrict__ xp, size_t rows, int HW, int HWp) {
+  const size_t total = rows * HWp;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / HWp;
+    const int c = (int)(i - r * HWp);
+    xp[i] = c < HW ? x[r * HW + c] : 0.f;
+  }
+}
+__global__ void unpad_cols_kernel(const float* __restrict__ xp, float* __restrict__ x, size_t rows, int HW, int HWp) {
+  const size_t total = rows * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / HW;
+    const int c = (int)(i - r * HW);
+    x[i] = xp[r * HWp + c];
+  }
+}
+static inline int pad4(int v) { return (v + 3) & ~3; }
+static int launch_pad(const float* x, float* xp, size_t rows, int HW, cudaStream_t st) {
+  pad_cols_kernel<<<148 * 8, 256, 0, st>>>(x, xp, rows, HW, pad4(HW));
+  HK_LAUNCH_CHECK("pad_cols_kernel");
+  return 0;
+}
+static int launch_unpad(const float* xp, float* x, size_t rows, int HW, cudaStream_t st) {
+  unpad_cols_kernel<<<148 * 8, 256, 0, st>>>(xp, x, rows, HW, pad4(HW));
+  HK_LAUNCH_CHECK("unpad_cols_kernel");
   return 0;
 }
 
@@ -470,7 +499,7 @@ __global__ void colsum_finish_kernel(const float* partial, float* s, int CS, int
   }
 }
 
-__global__ void norm_from_s_kernel(const float* s, float* inv_norm, int C, int HW) {
+__global__ void norm_from_s_kernel(const float* s, float* inv_norm, int C, int HW, float inv_hw) {
   const int b = blockIdx.x;
   __shared__ float red[32];
   float acc = 0.f;
@@ -484,21 +513,27 @@ __global__ void norm_from_s_kernel(const float* s, float* inv_norm, int C, int H
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-    const float nrm = sqrtf(t / (float)HW + (float)C * (float)C * 1e-5f);
+    const float nrm = sqrtf(t * inv_hw + (float)C * (float)C * 1e-5f);
     inv_norm[b] = 1.f / fmaxf(nrm, 1e-12f);
   }
 }
 
 }  // namespace hk
 
+namespace hk {
+static int bilinear_bwd_impl(const float* x, const float* dy, float* dx, int B, int C, int HW, float inv_hw, float* S,
+                             float* partial, float* svec, float* invn, float* craw, float* alpha, float* beta,
+                             cudaStream_t stream);
+}
+
 using namespace hk;
 
 extern "C" {
 
 size_t hk_bilinear_pool_fwd_workspace_bytes(int B, int C, int HW) {
-  // channel-sum partials [B][CS][HW] of the two-kernel path + inv_norm [B] at the end
-  (void)C;
-  return ((size_t)B * COLSUM_SPLITS * HW + B) * sizeof(float);
+  // channel-sum partials [B][CS][HWp] of the two-kernel path + inv_norm [B] (+ the zero-padded copy of x when H*W % 4 != 0)
+  const int HWp = pad4(HW);
+  return ((size_t)B * COLSUM_SPLITS * HWp + pad4(B) + (HWp != HW ? (size_t)B * C * HWp : 0)) * sizeof(float);
 }
 
 int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, int C, int HW, void* workspace,
@@ -509,14 +544,22 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
   HK_REQUIRE(y && aligned16(y), HK_ERR_ALIGN, "hk_bilinear_pool_fwd: output null/unaligned");
   HK_REQUIRE(workspace && workspace_bytes >= hk_bilinear_pool_fwd_workspace_bytes(B, C, HW), HK_ERR_WORKSPACE,
              "hk_bilinear_pool_fwd: workspace too small");
+  const float inv_hw = 1.f / (float)HW;              // normalisations use the true H*W ...
+  const int HWp = pad4(HW);
   float* partial = static_cast<float*>(workspace);
-  float* invn_ws = reinterpret_cast<float*>(static_cast<char*>(workspace) + hk_bilinear_pool_fwd_workspace_bytes(B, C, HW)) - B;
+  float* invn_ws = partial + (size_t)B * COLSUM_SPLITS * HWp;
   float* invn = inv_norm_out ? inv_norm_out : invn_ws;
+  if (HWp != HW) {                                   // ... the kernels' geometry the padded one
+    float* xp = invn_ws + pad4(B);                    // 16-byte aligned: TMA reads it
+    if ((r = launch_pad(x, xp, (size_t)B * C, HW, stream))) return r;
+    x = xp;
+    HW = HWp;
+  }
   if (precise()) {   // 3xTF32 Gram on the generic GEMM, then sqrt + L2 normalise in place; nothing rounded
     GemmEpi e = {};
     e.C = y; e.ldc = C; e.strideC = (long long)C * C; e.alpha = 1.f;
     if ((r = gemm_tf32(x, 0, HW, (long long)C * HW, x, 0, HW, (long long)C * HW, e, C, C, HW, B, stream))) return r;
-    bilinear_finish_kernel<<<B, 1024, 0, stream>>>(y, invn, C * C, 1.f / (float)HW, 1e-5f);
+    bilinear_finish_kernel<<<B, 1024, 0, stream>>>(y, invn, C * C, inv_hw, 1e-5f);
     HK_LAUNCH_CHECK("bilinear_finish_kernel");
     return 0;
   }
@@ -530,16 +573,16 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
     variant = (v && v[0] == 'c') ? 1 : ((v && v[0] == 't' && v[1] == 'w') ? 2 : 0);
   }
   if (variant == 1 && C == 512) {
-    r = bcnn_cluster_fwd(tm, y, invn, B, HW, stream);
+    r = bcnn_cluster_fwd(tm, y, invn, B, HW, inv_hw, stream);
     if (r != HK_ERR_UNSUPPORTED) return r;
   }
   if (variant != 2) {
-    r = bcnn_tiles_fwd(tm, x, y, invn, B, C, HW, stream);
+    r = bcnn_tiles_fwd(tm, x, y, invn, B, C, HW, inv_hw, stream);
     if (r != HK_ERR_UNSUPPORTED) return r;        // more tiles per image than the slot table holds: two-kernel path
   }
   GramArgs a = {};
   a.C = C; a.HW = HW; a.nblk = C / 128;
-  a.inv_hw = 1.f / (float)HW; a.eps = 1e-5f;
+  a.inv_hw = inv_hw; a.eps = 1e-5f;
   a.store_mode = 1; a.x_hint = 1;
   // general C: channel-sum pre-kernel + tile-pair Gram kernel, overlapped by programmatic dependent launch
   colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, colsum_smem(HW), stream>>>(x, partial, C, HW, COLSUM_SPLITS, nullptr, nullptr, 0);
@@ -550,8 +593,10 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
 }
 
 size_t hk_bilinear_pool_bwd_workspace_bytes(int B, int C, int HW) {
-  // S [B,C,C] + partial [B,CS,HW] + s [B,HW] + inv_norm,c_raw,alpha,beta [4B]
-  return ((size_t)B * C * C + (size_t)B * COLSUM_SPLITS * HW + (size_t)B * HW + 4 * (size_t)B + 64) * sizeof(float);
+  // S [B,C,C] + partial [B,CS,HWp] + s [B,HWp] + inv_norm,c_raw,alpha,beta [4B] (+ padded copies of x and dx when H*W % 4 != 0)
+  const int HWp = pad4(HW);
+  return ((size_t)B * C * C + (size_t)B * COLSUM_SPLITS * HWp + (size_t)B * HWp + 4 * (size_t)pad4(B) + 64 +
+          (HWp != HW ? 2 * (size_t)B * C * HWp : 0)) * sizeof(float);
 }
 
 int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int C, int HW, void* workspace,
@@ -562,13 +607,36 @@ int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int 
   HK_REQUIRE(dy && dx && aligned16(dy) && aligned16(dx), HK_ERR_ALIGN, "hk_bilinear_pool_bwd: null/unaligned pointer");
   HK_REQUIRE(workspace && workspace_bytes >= hk_bilinear_pool_bwd_workspace_bytes(B, C, HW), HK_ERR_WORKSPACE,
              "hk_bilinear_pool_bwd: workspace too small");
+  const float inv_hw = 1.f / (float)HW;
+  const int HW_true = HW, HWp = pad4(HW);
   float* S = static_cast<float*>(workspace);
   float* partial = S + (size_t)B * C * C;
-  float* svec = partial + (size_t)B * COLSUM_SPLITS * HW;
-  float* invn = svec + (size_t)B * HW;
-  float* craw = invn + B;
-  float* alpha = craw + B;
-  float* beta = alpha + B;
+  float* svec = partial + (size_t)B * COLSUM_SPLITS * HWp;
+  float* invn = svec + (size_t)B * HWp;
+  float* craw = invn + pad4(B);
+  float* alpha = craw + pad4(B);
+  float* beta = alpha + pad4(B);
+  float* dx_out = dx;
+  if (HWp != HW) {      // zero-padded copy of x; dx is produced padded and copied back at the end
+    float* xp = beta + pad4(B) + 64;
+    dx = xp + (size_t)B * C * HWp;
+    if ((r = launch_pad(x, xp, (size_t)B * C, HW, stream))) return r;
+    x = xp;
+    HW = HWp;
+  }
+  r = bilinear_bwd_impl(x, dy, dx, B, C, HW, inv_hw, S, partial, svec, invn, craw, alpha, beta, stream);
+  if (r || dx == dx_out) return r;
+  return launch_unpad(dx, dx_out, (size_t)B * C, HW_true, stream);
+}
+
+}  // extern "C"
+
+namespace hk {
+static int bilinear_bwd_impl(const float* x, const float* dy, float* dx, int B, int C, int HW, float inv_hw, float* S,
+                             float* partial, float* svec, float* invn, float* craw, float* alpha, float* beta,
+                             cudaStream_t stream) {
+  void* stream_ = stream;
+  int r;
   if (precise()) {
     colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, colsum_smem(HW), stream>>>(x, partial, C, HW, COLSUM_SPLITS, nullptr,
                                                                                   nullptr, 0, 0xffffffffu);
@@ -578,9 +646,9 @@ int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int 
     GemmEpi e = {};
     e.C = S; e.ldc = C; e.strideC = (long long)C * C; e.alpha = 1.f;
     if ((r = gemm_tf32(x, 0, HW, (long long)C * HW, x, 0, HW, (long long)C * HW, e, C, C, HW, B, stream))) return r;
-    bilinear_bwd_s_kernel<<<B, 1024, 0, stream>>>(S, dy, invn, craw, C, 1.f / (float)HW, 1e-5f);
+    bilinear_bwd_s_kernel<<<B, 1024, 0, stream>>>(S, dy, invn, craw, C, inv_hw, 1e-5f);
     HK_LAUNCH_CHECK("bilinear_bwd_s_kernel");
-    bilinear_bwd_scalars_kernel<<<(B + 127) / 128, 128, 0, stream>>>(invn, craw, 1.f / (float)HW, alpha, beta, B);
+    bilinear_bwd_scalars_kernel<<<(B + 127) / 128, 128, 0, stream>>>(invn, craw, inv_hw, alpha, beta, B);
     HK_LAUNCH_CHECK("bilinear_bwd_scalars_kernel");
     return hk_gemm_tf32(S, 0, C, (long long)C * C, x, 1, HW, (long long)C * HW, dx, HW, (long long)C * HW, 0, C, HW, C, B,
                         1.f, alpha, 0.f, svec, 0, HW, 1.f, beta, 0, stream_);
@@ -594,20 +662,19 @@ int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int 
   HK_LAUNCH_CHECK("colsum_finish_kernel");
   GramArgs a = {};
   a.B = B; a.C = C; a.HW = HW; a.nblk = C / 128;
-  a.inv_hw = 1.f / (float)HW; a.eps = 1e-5f;
+  a.inv_hw = inv_hw; a.eps = 1e-5f;
   a.dY = dy; a.S = S; a.c_raw = craw;
   if ((r = launch_gram<MODE_BCNN_BWD_S>(tm, a, stream))) return r;
-  norm_from_s_kernel<<<B, 256, 0, stream>>>(svec, invn, C, HW);
+  norm_from_s_kernel<<<B, 256, 0, stream>>>(svec, invn, C, HW, inv_hw);
   HK_LAUNCH_CHECK("norm_from_s_kernel");
-  bilinear_bwd_scalars_kernel<<<(B + 127) / 128, 128, 0, stream>>>(invn, craw, 1.f / (float)HW, alpha, beta, B);
+  bilinear_bwd_scalars_kernel<<<(B + 127) / 128, 128, 0, stream>>>(invn, craw, inv_hw, alpha, beta, B);
   HK_LAUNCH_CHECK("bilinear_bwd_scalars_kernel");
   // dX = alpha_b * (S . X) + beta_b * 1 s^T      (M=C, K=C, N=HW; X is the MN-major B operand); rounded to tf32: it is
   // the dY operand of the last conv's dgrad / wgrad MMAs
   return hk_gemm_tf32(S, 0, C, (long long)C * C, x, 1, HW, (long long)C * HW, dx, HW, (long long)C * HW, 0, C, HW, C, B,
                       1.f, alpha, 0.f, svec, 0, HW, 1.f, beta, 2, stream_);
 }
-
-}  // extern "C"
+}  // namespace hk
 
 
 // =====================================================================================================
@@ -707,6 +774,13 @@ int hk_cbp_fwd(const float* x, const int* h1, const int* h2, const float* s1, co
   int r = check_gram_shape("hk_cbp_fwd", x, B, C, HW);
   if (r) return r;
   HK_REQUIRE(h1 && h2 && s1 && s2 && y && pre && d > 0, HK_ERR_ARG, "hk_cbp_fwd: null pointer / bad d");
+  Scratch xpad(pad4(HW) != HW ? (size_t)B * C * pad4(HW) * sizeof(float) : 16, stream);   // H*W % 4 != 0 only
+  if (pad4(HW) != HW) {
+    HK_REQUIRE(xpad.p, HK_ERR_DRIVER, "hk_cbp_fwd: cudaMallocAsync of the padded input failed");
+    if ((r = launch_pad(x, xpad.f(), (size_t)B * C, HW, stream))) return r;
+    x = xpad.f();
+    HW = pad4(HW);
+  }
   cudaError_t e = cudaMemsetAsync(pre, 0, (size_t)B * d * sizeof(float), stream);
   if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(pre): %s", cudaGetErrorString(e));
   if (precise()) {   // 3xTF32 Gram on the generic GEMM, scattered into the bins by a plain kernel
@@ -744,6 +818,13 @@ int hk_cbp_bwd(const float* x, const float* pre, const float* dy, const int* h1,
   HK_REQUIRE(pre && dy && dx && h1 && h2 && s1 && s2, HK_ERR_ARG, "hk_cbp_bwd: null pointer");
   HK_REQUIRE(workspace && workspace_bytes >= hk_cbp_bwd_workspace_bytes(B, C, d), HK_ERR_WORKSPACE,
              "hk_cbp_bwd: workspace too small");
+  const int HWp = pad4(HW);
+  Scratch xpad(HWp != HW ? (size_t)B * C * HWp * sizeof(float) : 16, stream);             // H*W % 4 != 0 only
+  if (HWp != HW) {
+    HK_REQUIRE(xpad.p, HK_ERR_DRIVER, "hk_cbp_bwd: cudaMallocAsync of the padded input failed");
+    if ((r = launch_pad(x, xpad.f(), (size_t)B * C, HW, stream))) return r;
+    x = xpad.f();
+  }
   float* S = static_cast<float*>(workspace);
   float* dpre = S + (size_t)B * C * C;
   cbp_finalize_bwd_kernel<<<B, 256, 0, stream>>>(pre, dy, dpre, d);
@@ -751,7 +832,7 @@ int hk_cbp_bwd(const float* x, const float* pre, const float* dy, const int* h1,
   cbp_build_s_kernel<<<dim3(148, B), 256, 0, stream>>>(dpre, h1, h2, s1, s2, S, C, d, precise() ? 0 : 1);
   HK_LAUNCH_CHECK("cbp_build_s_kernel");
   // dX = (dG + dG^T) . X      (M = C, K = C, N = HW; X is the MN-major B operand)
-  return hk_gemm_tf32(S, 0, C, (long long)C * C, x, 1, HW, (long long)C * HW, dx, HW, (long long)C * HW, 0, C, HW, C, B,
+  return hk_gemm_tf32(S, 0, C, (long long)C * C, x, 1, HWp, (long long)C * HWp, dx, HW, (long long)C * HW, 0, C, HW, C, B,
                       1.f, nullptr, 0.f, nullptr, 0, 0, 0.f, nullptr, 2, stream_);
 }
 

@@ -690,6 +690,175 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// wgrad, version 2: the dY tile (A operand, 128 co x 64 pixels) is reused by all nine taps, yet in the SS form every one of
+// the 3 (+1 bias) MMAs of a k-step re-reads it from shared memory: (4 KB A + 3 KB B) per 48-cycle N=96 MMA = 146 B/clk
+// against a 128 B/clk shared-memory port — the kernel was shared-memory-bound, not tensor-bound.  Here the four otherwise
+// idle epilogue warps transpose each dY tile ONCE from shared memory into tensor memory (thread = co, 64 pixel columns,
+// tcgen05.st) and the MMAs take A from TMEM (tcgen05.mma [tmem], b-desc): shared-memory traffic per k-step drops from 21 KB
+// to 9 KB + a 4 KB one-off read.  dY is TMA-loaded with the plain 128B swizzle (it is no longer a UMMA smem operand).
+// TMEM: tap accumulators 0..287, bias 288..303, A double buffer 320..447.
+// ------------------------------------------------------------------------------------------------
+constexpr int WG2_BIAS_COL = 288;
+constexpr int WG2_A_COL = 320;
+
+__global__ void __launch_bounds__(192, 1)
+conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, WgradArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + WG_STAGES * WG_A_BYTES;
+  float* ones = reinterpret_cast<float*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES + WG_ONES_BYTES);
+  uint64_t* empty = full + WG_STAGES;
+  uint64_t* accf = empty + WG_STAGES;
+  uint64_t* a_ready = accf + 1;     // [2] stager warps (4) -> MMA: dY tile kb is in TMEM buffer kb & 1
+  uint64_t* a_free = a_ready + 2;   // [2] MMA (tcgen05.commit) -> stagers: the MMAs reading buffer kb & 1 have retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_free + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_ci_tiles = a.Cin / 32;
+  const int ci_t = blockIdx.x % n_ci_tiles, co_t = blockIdx.x / n_ci_tiles;
+  const int split = blockIdx.y;
+  const int co0 = co_t * 128, ci0 = ci_t * 32;
+  const bool do_bias = (a.db != nullptr) && (ci_t == 0);
+  const long long total_tiles = (long long)a.tiles_w * a.tiles_h * a.tiles_n;
+  const long long per = (total_tiles + a.ksplit - 1) / a.ksplit;
+  const long long t_begin = per * split;
+  const long long t_end = (t_begin + per < total_tiles) ? t_begin + per : total_tiles;
+  const int nk = (int)(t_end > t_begin ? t_end - t_begin : 0);
+  const int img_rows = a.TH * a.TW;
+  const int patch_rows = (a.TH + 2) * a.TW;
+  const int ksteps_img = img_rows / 8;
+
+  for (int i = threadIdx.x; i < WG_ONES_BYTES / 4; i += blockDim.x) ones[i] = 1.f;
+  fence_proxy_async();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accf, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_ready[i], 4); mbar_init(&a_free[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nk > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int kb = 0; kb < nk; ++kb) {
+          const int s = kb % WG_STAGES;
+          const uint32_t ph = (kb / WG_STAGES) & 1;
+          int tt = (int)t_begin + kb;
+          const int tw = tt % a.tiles_w; tt /= a.tiles_w;
+          const int th = tt % a.tiles_h; tt /= a.tiles_h;
+          const int w0 = tw * a.TW, h0 = th * a.TH, n0 = tt * a.TN;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], WG_A_BYTES + 3 * patch_rows * a.TN * 128);
+          uint8_t* pa = sA + s * WG_A_BYTES;
+          uint8_t* pb = sB + s * WG_B_BYTES;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_4d(pa + j * WG_KP * 128, &tmDY, &full[s], co0 + j * 32, w0, h0, n0);
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) tma_load_4d(pb + kw * WG_B_ONE, &tmX, &full[s], ci0, w0 + kw - 1, h0 - 1, n0);
+        }
+      }
+    } else if (warp == 1) {
+      const uint32_t idesc = make_idesc_tf32(128, 96, 0, 1);
+      const uint32_t idesc_b = make_idesc_tf32(128, 16, 0, 1);
+      const uint64_t ones_desc = make_sdesc_mn(smem_u32(ones), 0);
+      uint32_t b_off[8];
+      {
+        int ks = 0;
+        for (int n = 0; n < a.TN; ++n)
+          for (int j = 0; j < ksteps_img; ++j, ++ks) b_off[ks] = (uint32_t)((n * patch_rows + j * 8) * 128) >> 4;
+      }
+      const uint32_t kh_step = (uint32_t)(a.TW * 128) >> 4;
+      const uint64_t b_tmpl = make_sdesc_mn(0, WG_B_ONE);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % WG_STAGES;
+        const uint32_t ph = (kb / WG_STAGES) & 1;
+        const int ab = kb & 1;
+        mbar_wait(&full[s], ph);                       // the X patches of this stage have landed
+        mbar_wait(&a_ready[ab], (kb >> 1) & 1);        // ... and its dY tile is in tensor memory
+        tc_fence_after();
+        const uint64_t b_base = b_tmpl + (smem_u32(sB + s * WG_B_BYTES) >> 4);
+        const uint32_t a_tm = tmem_base + WG2_A_COL + ab * WG_KP;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t accum = (kb | ks) ? 1u : 0u;
+            const uint32_t ad = a_tm + ks * 8;
+            const uint64_t bd = b_base + b_off[ks];
+            umma_tf32_ts(tmem_base, ad, bd, idesc, accum);
+            umma_tf32_ts(tmem_base + 96, ad, bd + kh_step, idesc, accum);
+            umma_tf32_ts(tmem_base + 192, ad, bd + 2 * kh_step, idesc, accum);
+            if (do_bias) umma_tf32_ts(tmem_base + WG2_BIAS_COL, ad, ones_desc, idesc_b, accum);
+          }
+          umma_commit(&empty[s]);
+          umma_commit(&a_free[ab]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(accf);
+      __syncwarp();
+    } else {
+      // ---- stagers (main loop), then epilogue.  warp -> TMEM lane quarter q = co block of 32; thread = one co
+      const int q = warp & 3;
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % WG_STAGES;
+        const uint32_t ph = (kb / WG_STAGES) & 1;
+        const int ab = kb & 1;
+        mbar_wait(&full[s], ph);
+        // co block q of the tile: 64 pixel rows x 128 B, 128B-swizzled (16-byte chunk ^ (row & 7)); lane = word in the row
+        const uint8_t* tile = sA + s * WG_A_BYTES + q * (WG_KP * 128);
+        float v0[32], v1[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          v0[k] = *reinterpret_cast<const float*>(tile + k * 128 + ((((lane >> 2) ^ (k & 7)) << 4) | ((lane & 3) << 2)));
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          v1[k] = *reinterpret_cast<const float*>(tile + (32 + k) * 128 + ((((lane >> 2) ^ (k & 7)) << 4) | ((lane & 3) << 2)));
+        if (kb >= 2) { mbar_wait(&a_free[ab], ((kb >> 1) - 1) & 1); tc_fence_after(); }
+        const uint32_t dst = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + WG2_A_COL + ab * WG_KP;
+        tmem_st32(dst, v0);
+        tmem_st32(dst + 32, v1);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[ab]);
+      }
+      const int co = co0 + q * 32 + lane;
+      mbar_wait(accf, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tap * 32, v);
+        tmem_ld_wait();
+        if (co < a.Cout) {
+          float* dst = a.dWp + ((size_t)tap * a.Cout + co) * a.Cin + ci0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+        }
+      }
+      if (do_bias) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + WG2_BIAS_COL, v);
+        tmem_ld_wait();
+        if (co < a.Cout) atomicAdd(a.db + co, v[0]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // pixel tile for wgrad: TW in {4,8,16} (kh shifts must be whole 512 B swizzle atoms), TW*TH*TN = 64, TH*TW % 8 == 0
 static bool pick_wgrad_tile(int W, int H, int* TW, int* TH, int* TN) {
   int tw = 0;
@@ -766,9 +935,11 @@ static int conv3x3_wgrad_1x(const float* x, const float* dy, float* dwp, float* 
   if (ks > 65535) ks = 65535;
   a.ksplit = (int)ks;
   { const char* v = getenv("HK_DBG_WG"); a.dbg = v ? atoi(v) : 0; }
+  static int use_v2 = -1;
+  if (use_v2 < 0) { const char* v = getenv("HK_WGRAD_V2"); use_v2 = v ? atoi(v) : 1; }
   CUtensorMap tmDY, tmX;
   int r;
-  if ((r = make_act_map(&tmDY, dy, N, H, W, Cout, a.TW, a.TH, a.TN, true))) return r;
+  if ((r = make_act_map(&tmDY, dy, N, H, W, Cout, a.TW, a.TH, a.TN, /*mn_major=*/!use_v2))) return r;
   if ((r = make_act_map(&tmX, x, N, H, W, Cin, a.TW, a.TH + 2, a.TN, true))) return r;
   cudaError_t e = cudaSuccess;
   if (zero_dw) {
@@ -782,11 +953,13 @@ static int conv3x3_wgrad_1x(const float* x, const float* dy, float* dwp, float* 
   static bool attr_set = false;
   if (!attr_set) {
     e = cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_wgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
     if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((unsigned)out_tiles, a.ksplit);
-  conv3x3_wgrad_kernel<<<grid, 192, WG_SMEM, stream>>>(tmDY, tmX, a);
+  if (use_v2) conv3x3_wgrad_v2_kernel<<<grid, 192, WG_SMEM, stream>>>(tmDY, tmX, a);
+  else conv3x3_wgrad_kernel<<<grid, 192, WG_SMEM, stream>>>(tmDY, tmX, a);
   HK_LAUNCH_CHECK("conv3x3_wgrad_kernel");
   return 0;
 }

@@ -312,16 +312,17 @@ static size_t operand_extent(long long rows, long long cols, long long ld, long 
 
 // 3xTF32: A.B ~= Ah.Bh + Al.Bh + Ah.Bl with (hi, lo) = tf32 halves of the operands, chained through the epilogue's raw
 // addend E so the caller's epilogue (alpha, diag, D, ReLU, transposed store ...) is applied once, to the full sum.
-static int gemm_tf32_3x(const float* A, int a_mn, long long lda, long long strideA, const float* B, int b_mn, long long ldb,
+int gemm_tf32_3x(const float* A, int a_mn, long long lda, long long strideA, const float* B, int b_mn, long long ldb,
                         long long strideB, const GemmEpi& epi, int M, int N, int K, int batch, cudaStream_t st) {
   const size_t nA = operand_extent(a_mn ? K : M, a_mn ? M : K, lda, strideA, batch);
   const bool same = (A == B && a_mn == b_mn && lda == ldb && strideA == strideB && M == N);
   const size_t nB = same ? 0 : operand_extent(b_mn ? K : N, b_mn ? N : K, ldb, strideB, batch);
-  Scratch sa(2 * nA * sizeof(float), st), sb(2 * (nB ? nB : 4) * sizeof(float), st);
+  const size_t nA4 = (nA + 3) & ~size_t(3), nB4 = (nB + 3) & ~size_t(3);     // the lo halves start 16-byte aligned (TMA)
+  Scratch sa(2 * nA4 * sizeof(float), st), sb(2 * (nB4 ? nB4 : 4) * sizeof(float), st);
   Scratch tmp((size_t)batch * M * N * sizeof(float), st);
   HK_REQUIRE(sa.p && sb.p && tmp.p, HK_ERR_DRIVER, "gemm (precise): cudaMallocAsync of the operand halves failed");
-  float *Ah = sa.f(), *Al = Ah + nA;
-  float *Bh = same ? Ah : sb.f(), *Bl = same ? Al : Bh + nB;
+  float *Ah = sa.f(), *Al = Ah + nA4;
+  float *Bh = same ? Ah : sb.f(), *Bl = same ? Al : Bh + nB4;
   int r;
   if ((r = tf32_split(A, Ah, Al, nA, st))) return r;
   if (!same && (r = tf32_split(B, Bh, Bl, nB, st))) return r;
@@ -363,6 +364,24 @@ int gemm_tf32_1x(const float* A, int a_mn, long long lda, long long strideA, con
 }
 
 }  // namespace hk
+
+// same signature as hk_gemm_tf32, always 3xTF32 (callers whose result feeds an exponential: CIN's softmax(-Gram))
+extern "C" int hk_gemm_3xtf32(const float* A, int a_mn_major, long long lda, long long strideA, const float* B,
+                              int b_mn_major, long long ldb, long long strideB, float* C, long long ldc,
+                              long long strideC, int trans_c, int M, int N, int K, int batch, float alpha,
+                              const float* alpha_vec, float diag, const float* D, long long ldd, long long strideD,
+                              float beta, const float* beta_vec, int relu, void* stream) {
+  hk::GemmEpi epi;
+  epi.C = C; epi.ldc = ldc; epi.strideC = strideC;
+  epi.D = D; epi.ldd = ldd; epi.strideD = strideD;
+  epi.alpha_vec = alpha_vec; epi.beta_vec = beta_vec;
+  epi.alpha = alpha; epi.beta = beta; epi.diag = diag;
+  epi.trans_c = trans_c; epi.relu = relu;
+  epi.C_lo = nullptr; epi.D_lo = nullptr; epi.E = nullptr; epi.ldE = 0; epi.strideE = 0;
+  HK_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, HK_ERR_ARG, "hk_gemm_3xtf32: bad args");
+  return hk::gemm_tf32_3x(A, a_mn_major, lda, strideA, B, b_mn_major, ldb, strideB, epi, M, N, K, batch,
+                          static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int hk_gemm_tf32(const float* A, int a_mn_major, long long lda, long long strideA, const float* B,
                             int b_mn_major, long long ldb, long long strideB, float* C, long long ldc,

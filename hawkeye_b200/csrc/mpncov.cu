@@ -40,13 +40,14 @@ static int mm3(Pair A, Pair B, Pair C, float* tmp, int n, int batch, float alpha
 
 // ------------------------------------------------------------------------------------------------ small kernels
 // centre the rows of X [B*C][M] (subtract the spatial mean) and round to tf32:  X I_hat X^T = Xc Xc^T / M
-__global__ void center_rows_kernel(const float* __restrict__ x, float* __restrict__ xc, int M, int round) {
+__global__ void center_rows_kernel(const float* __restrict__ x, float* __restrict__ xc, int M, int Mp, int round) {
   const size_t row = blockIdx.x;
   const float* p = x + row * M;
   float s = 0.f;
   for (int i = threadIdx.x; i < M; i += 32) s += p[i];
   s = warp_sum(s) / (float)M;
-  for (int i = threadIdx.x; i < M; i += 32) xc[row * M + i] = round ? tf32_round(p[i] - s) : p[i] - s;
+  for (int i = threadIdx.x; i < Mp; i += 32)       // columns M..Mp-1 (pitch padding for TMA) stay zero: they add nothing
+    xc[row * Mp + i] = i < M ? (round ? tf32_round(p[i] - s) : p[i] - s) : 0.f;
 }
 
 // normA[b] = trace(x[b]); A = x / normA as a (hi, lo) pair
@@ -163,25 +164,26 @@ extern "C" {
 int hk_covpool_fwd(const float* x, float* cov, float* xc, int B, int C, int M, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   HK_REQUIRE(x && cov && xc, HK_ERR_ARG, "hk_covpool_fwd: null pointer");
-  HK_REQUIRE(M % 4 == 0, HK_ERR_UNSUPPORTED, "hk_covpool_fwd: H*W=%d must be a multiple of 4", M);
-  center_rows_kernel<<<(unsigned)((size_t)B * C), 32, 0, st>>>(x, xc, M, precise() ? 0 : 1);
+  const int Mp = (M + 3) & ~3;                      // xc is [B, C, Mp]: centred rows at a 16-byte pitch
+  center_rows_kernel<<<(unsigned)((size_t)B * C), 32, 0, st>>>(x, xc, M, Mp, precise() ? 0 : 1);
   HK_LAUNCH_CHECK("center_rows_kernel");
   GemmEpi e = {};
   e.C = cov; e.ldc = C; e.strideC = (long long)C * C; e.alpha = 1.f / (float)M;
-  return gemm_tf32(xc, 0, M, (long long)C * M, xc, 0, M, (long long)C * M, e, C, C, M, B, st);
+  return gemm_tf32(xc, 0, Mp, (long long)C * Mp, xc, 0, Mp, (long long)C * Mp, e, C, C, Mp, B, st);
 }
 
 int hk_covpool_bwd(const float* xc, const float* g, float* dx, int B, int C, int M, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   HK_REQUIRE(xc && g && dx, HK_ERR_ARG, "hk_covpool_bwd: null pointer");
-  // dX = (g + g^T) X I_hat = (g . Xc + g^T . Xc) / M
+  const int Mp = (M + 3) & ~3;
+  // dX = (g + g^T) X I_hat = (g . Xc + g^T . Xc) / M        (xc pitch Mp, dx pitch M)
   GemmEpi e = {};
   e.C = dx; e.ldc = M; e.strideC = (long long)C * M; e.alpha = 1.f;
-  int r = gemm_tf32(g, 0, C, (long long)C * C, xc, 1, M, (long long)C * M, e, C, M, C, B, st);   // raw g . Xc
+  int r = gemm_tf32(g, 0, C, (long long)C * C, xc, 1, Mp, (long long)C * Mp, e, C, M, C, B, st);   // raw g . Xc
   if (r) return r;
   e.E = dx;   // (g^T . Xc + g . Xc) / M
   e.alpha = 1.f / (float)M;
-  return gemm_tf32(g, 1, C, (long long)C * C, xc, 1, M, (long long)C * M, e, C, M, C, B, st);
+  return gemm_tf32(g, 1, C, (long long)C * C, xc, 1, Mp, (long long)C * Mp, e, C, M, C, B, st);
 }
 
 /* ---------------- Sqrtm (MPNCOV.py:137-202) ---------------- */

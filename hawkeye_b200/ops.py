@@ -374,7 +374,7 @@ class CovpoolFn(Function):
         x = _f32c(x)
         B, C, H, W = x.shape
         cov = torch.empty(B, C, C, device=x.device, dtype=torch.float32)
-        xc = torch.empty(B, C, H * W, device=x.device, dtype=torch.float32)
+        xc = torch.empty(B, C, (H * W + 3) // 4 * 4, device=x.device, dtype=torch.float32)   # centred rows, 16-byte pitch
         _lib.call('hk_covpool_fwd', x, cov, xc, B, C, H * W, _lib.stream_ptr())
         ctx.save_for_backward(xc)
         ctx.shape = x.shape

@@ -9,8 +9,9 @@ from . import _lib
 from .ops import _check_cuda, _f32c, _ws
 
 
-def _gemm(A, a_mn, lda, sA, B, b_mn, ldb, sB, C, ldc, sC, M, N, K, batch, alpha=1.0, D=None, ldd=0, sD=0, beta=0.0):
-    _lib.call('hk_gemm_tf32', A, int(a_mn), lda, sA, B, int(b_mn), ldb, sB, C, ldc, sC, 0, M, N, K, batch, float(alpha), None,
+def _gemm(A, a_mn, lda, sA, B, b_mn, ldb, sB, C, ldc, sC, M, N, K, batch, alpha=1.0, D=None, ldd=0, sD=0, beta=0.0,
+          exact=False):
+    _lib.call('hk_gemm_3xtf32' if exact else 'hk_gemm_tf32', A, int(a_mn), lda, sA, B, int(b_mn), ldb, sB, C, ldc, sC, 0, M, N, K, batch, float(alpha), None,
               0.0, D, ldd, sD, float(beta), None, 0, _lib.stream_ptr())
 
 
@@ -23,7 +24,8 @@ class GramFn(Function):
         x = _f32c(x)
         B, C, P = x.shape
         g = torch.empty(B, C, C, device=x.device, dtype=torch.float32)
-        _gemm(x, 0, P, C * P, x, 0, P, C * P, g, C, C * C, C, C, P, B, alpha)
+        # 3xTF32: G feeds exp(-G) with |G| in the tens — a 5e-4 relative TF32 error would be percents of the softmax
+        _gemm(x, 0, P, C * P, x, 0, P, C * P, g, C, C * C, C, C, P, B, alpha, exact=True)
         ctx.save_for_backward(x)
         ctx.alpha = alpha
         return g

@@ -47,9 +47,16 @@ int hk_gemm_tf32(const float* A, int a_mn_major, long long lda, long long stride
                  int N, int K, int batch, float alpha, const float* alpha_vec, float diag, const float* D,
                  long long ldd, long long strideD, float beta, const float* beta_vec, int relu, void* stream);
 
+/* same product, always as 3xTF32 whatever the precision mode (results that feed an exponential, e.g. CIN's softmax(-Gram)) */
+int hk_gemm_3xtf32(const float* A, int a_mn_major, long long lda, long long strideA, const float* B, int b_mn_major,
+                   long long ldb, long long strideB, float* C, long long ldc, long long strideC, int trans_c, int M,
+                   int N, int K, int batch, float alpha, const float* alpha_vec, float diag, const float* D,
+                   long long ldd, long long strideD, float beta, const float* beta_vec, int relu, void* stream);
+
 /* ---- BCNN bilinear pooling: model/methods/BCNN.py:13-27 (BilinearPooling.forward) ----------------
  * x [B,C,HW] (NCHW feature map viewed as in BCNN.py:17) -> y [B,C*C] = normalize(sqrt(x x^T/HW + 1e-5)).
- * inv_norm_out (optional, [B]) receives 1/||z||.  Requires C%128==0, HW%4==0. */
+ * inv_norm_out (optional, [B]) receives 1/||z||.  Requires C%128==0.  H*W need not be a multiple of 4 (7x7 maps of 224x224
+ * inputs): the workspace then also holds a zero-padded copy of x (TMA needs a 16-byte row pitch). */
 size_t hk_bilinear_pool_fwd_workspace_bytes(int B, int C, int HW);
 int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, int C, int HW, void* workspace,
                          size_t workspace_bytes, void* stream);
@@ -63,7 +70,8 @@ int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int 
 /* ---- CBCNN compact bilinear pooling: model/methods/CBCNN.py:96-135 (CompactBilinearPooling.forward) ------------
  * h1,h2 int32 [C] and s1,s2 fp32 [C] are the count-sketch hash / sign vectors of CBCNN.py:76-91 (numpy seeds 1/3/5/7,
  * generated bit-exactly on the host).  y [B,d] = normalize(signed_sqrt(tensor-sketch)); pre [B,d] (pre-sqrt sketch)
- * is saved for the backward.  Requires C%128==0, HW%4==0. */
+ * is saved for the backward.  Requires C%128==0; for H*W % 4 != 0 a zero-padded copy of x is made in stream-ordered
+ * scratch (cudaMallocAsync) — the one case outside the precise mode where the library allocates. */
 int hk_cbp_fwd(const float* x, const int* h1, const int* h2, const float* s1, const float* s2, float* y, float* pre,
                int B, int C, int HW, int d, void* stream);
 size_t hk_cbp_bwd_workspace_bytes(int B, int C, int d);
@@ -72,7 +80,8 @@ int hk_cbp_bwd(const float* x, const float* pre, const float* dy, const int* h1,
                void* stream);
 
 /* ---- Fast MPN-COV pooling head: model/methods/MPNCOV.py:105-230 -----------------------------------------------
- * Covpool (:105-134): x [B,C,M] -> cov [B,C,C] = X I_hat X^T; xc [B,C,M] receives the centred features (saved for bwd).
+ * Covpool (:105-134): x [B,C,M] -> cov [B,C,C] = X I_hat X^T; xc [B,C,ceil4(M)] receives the centred features at a 16-byte row
+ *   pitch (saved for bwd; equal to [B,C,M] whenever M % 4 == 0).
  * Sqrtm (:137-202): coupled Newton-Schulz, iterN >= 2, forward and the reference's hand-derived backward formulae,
  *   all products as 3xTF32 tcgen05 GEMMs.  `saved` (hk_sqrtm_saved_floats floats) carries A, Y_i, Z_i, normA.
  * Triuvec (:205-230): row-major upper triangle [B,n,n] <-> [B,n(n+1)/2]. */

@@ -1,6 +1,7 @@
 """Golden fixtures at the BASELINE configuration (448x448, batch 2, 200 classes; BASELINE.json configs[0..3]) from the
 UNMODIFIED reference: BCNN stage 1/2, CBCNN d=8192 and d=6000, MPN.  Run here only (needs /root/reference):
     python tests/golden/make_golden_448.py   -> tests/golden/reference_448.npz
+    HK_GOLDEN_SIZE=224 python tests/golden/make_golden_448.py   -> tests/golden/reference_224.npz
 Inputs and weights are regenerated from tests/detgen.py seeds by the tests; the fixture carries outputs only:
 logits, loss, classifier gradients (bias, strided weight slice) and a few backbone gradients (whole small tensors, strided
 slices of large ones).
@@ -29,7 +30,8 @@ from model.registry import MODEL  # noqa: E402
 
 torch.set_num_threads(8)
 out = {}
-SIZE, B = 448, 2
+SIZE, B = int(os.environ.get('HK_GOLDEN_SIZE', '448')), 2      # 224: the 7x7 (H*W = 49, not a multiple of 4) maps of the
+#                                                                  reference's stock MPN / CBCNN / PeerLearning configs
 
 
 def rel_l2(a, b):
@@ -118,5 +120,5 @@ out['mpn_g_backbone.5.0.downsample.0.weight_slice'] = named['backbone.5.0.downsa
 uncertainties('mpn', lambda xx, s_: O.mpn_forward(xx, s_, 5), xm, lm, detgen.state_like(net), set(named.keys()))
 print('mpn', float(out['mpn_loss']), {k: float(v) for k, v in out.items() if k.startswith('mpn_u_')}, flush=True)
 
-np.savez_compressed(os.path.join(HERE, 'reference_448.npz'), **out)
-print('wrote', len(out), 'arrays;', os.path.getsize(os.path.join(HERE, 'reference_448.npz')) / 1e6, 'MB')
+np.savez_compressed(os.path.join(HERE, f'reference_{SIZE}.npz'), **out)
+print('wrote', len(out), 'arrays;', os.path.getsize(os.path.join(HERE, f'reference_{SIZE}.npz')) / 1e6, 'MB')

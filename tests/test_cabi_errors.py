@@ -32,7 +32,10 @@ def test_bilinear_pool_argument_errors(lib):
     f = lib.hk_bilinear_pool_fwd
     assert f(None, FAKE, None, 2, 512, 196, FAKE, 1 << 30, None) == -1 and 'null' in err(lib)
     assert f(FAKE, FAKE, None, 2, 100, 196, FAKE, 1 << 30, None) == -3 and 'multiple of 128' in err(lib)
-    assert f(FAKE, FAKE, None, 2, 512, 195, FAKE, 1 << 30, None) == -3 and 'multiple of 4' in err(lib)
+    # H*W % 4 != 0 is supported (zero-padded copy in the workspace): the workspace query grows accordingly
+    q = lib.hk_bilinear_pool_fwd_workspace_bytes
+    q.restype = ctypes.c_size_t
+    assert q(2, 512, 49) > q(2, 512, 52) and f(FAKE, FAKE, None, 2, 512, 49, FAKE, q(2, 512, 52), None) == -4
     assert f(FAKE + 4, FAKE, None, 2, 512, 196, FAKE, 1 << 30, None) == -2 and 'aligned' in err(lib)
     assert f(FAKE, FAKE, None, 2, 512, 196, FAKE, 16, None) == -4 and 'workspace' in err(lib)
     assert f(FAKE, FAKE, None, 0, 512, 196, FAKE, 1 << 30, None) == -1
@@ -56,7 +59,7 @@ def test_head_and_mpncov_argument_errors(lib):
     assert lib.hk_softmax_ce_ls(None, FAKE, FAKE, None, None, 2, 200, ctypes.c_float(0.1), ctypes.c_float(1.0), None) == -1
     assert lib.hk_sgd_momentum(FAKE, FAKE + 4, FAKE, 64, ctypes.c_float(0.1), ctypes.c_float(0.9), ctypes.c_float(0.0),
                                ctypes.c_float(1.0), 1, None) == -2
-    assert lib.hk_covpool_fwd(FAKE, FAKE, FAKE, 2, 256, 195, None) == -3
+    assert lib.hk_covpool_fwd(None, FAKE, FAKE, 2, 256, 195, None) == -1
     assert lib.hk_sqrtm_fwd(FAKE, FAKE, FAKE, 2, 256, 1, FAKE, 1 << 40, None) == -3 and 'iterN' in err(lib)
 
 
