@@ -39,7 +39,7 @@ RESNET50_MPN_FWD_GFLOP_PER_IMG = 32.9
 MPNCOV_GFLOP_PER_IMG = 1.77         # covariance + 5-iteration Newton-Schulz, forward + backward
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/ (see
 # profiles/README.md for the file each number comes from); None = not captured for this build
-K1_DRAM_TRAFFIC = {32: None, 256: None}
+K1_DRAM_TRAFFIC = {32: 12.89e6, 256: 102.82e6 + 209.68e6}     # profiles/gram_r2f_metrics.txt (tests/prof_bilinear.py 32 / 256)
 WORKLOADS = {
     'bcnn_s2': dict(cfg='BCNN_S2.yaml', trainer='BCNN', model='BCNN VGG-16 stage 2', fwd_gflop=VGG16_FWD_GFLOP_PER_IMG, bwd_mult=3.0),
     'bcnn_s1': dict(cfg='BCNN_S1.yaml', trainer='BCNN', model='BCNN VGG-16 stage 1 (classifier only)', fwd_gflop=VGG16_FWD_GFLOP_PER_IMG, bwd_mult=1.0),
@@ -394,6 +394,9 @@ def main():
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs only')
     ap.add_argument('--no-micro', action='store_true', help='skip the kernel micro-benchmarks (roofline legs)')
     ap.add_argument('--no-eager', action='store_true', help='skip the stock-PyTorch eager GPU leg')
+    ap.add_argument('--graph', default='auto', choices=['auto', '0', '1'],
+                    help='replay forward+backward from a CUDA graph (Trainer cuda_graph mode); auto = only for the '
+                         'host-launch-bound ResNet-50 workload')
     args = ap.parse_args()
     if args.workload is None:
         args.workload = f'bcnn_s{args.stage}'
@@ -405,6 +408,8 @@ def main():
     from hawkeye_b200.config import load_config
 
     os.environ.setdefault('HAWKEYE_ALLOW_RANDOM_INIT', '1')     # random-init weights are the benchmark's contract
+    use_graph = args.graph == '1' or (args.graph == 'auto' and args.workload == 'mpn')
+    os.environ['HK_CUDA_GRAPH'] = '1' if use_graph else '0' 
     W = WORKLOADS[args.workload]
     rank, local, world = engine.init_distributed()
     torch.cuda.set_device(local)
@@ -420,11 +425,14 @@ def main():
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
     def step_resident():
-        out = tr.model(x_dev)
-        loss = tr.criterion(out, y_dev)
-        tr.optimizer.zero_grad()
-        loss.backward()
-        tr.allreduce.finish()
+        if tr._graph_wanted():           # eager for three steps, captured on the third, replayed from then on
+            _, loss = tr._graph_step(x_dev, y_dev)
+        else:
+            out = tr.model(x_dev)
+            loss = tr.criterion(out, y_dev)
+            tr.optimizer.zero_grad()
+            loss.backward()
+            tr.allreduce.finish()
         tr.optimizer.step()
         return loss
 
@@ -446,7 +454,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    warm = max(args.warmup, 3)
+    warm = max(args.warmup, 5 if use_graph else 3)
     for _ in range(warm):
         loss = step_resident()
     torch.cuda.synchronize()
@@ -481,7 +489,7 @@ def main():
         'warmup': warm, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'tf32 (fp32 storage, fp32 accumulate)', 'data': 'synthetic',
         'config': {'workload': f'{W["model"]}, 448x448, batch {B}/GPU, 200 classes ({W["cfg"]})',
-                   'global_batch': B * world, 'parallelism': f'dp{world}',
+                   'global_batch': B * world, 'parallelism': f'dp{world}', 'cuda_graph': bool(use_graph),
                    'l2': 'per-step working set (GBs of activations) >> 126 MB L2; kernel microbenches rotate through buffer '
                          'sets totalling >= 640 MB (5x L2), so every launch reads cold inputs',
                    'final_loss': final_loss},

@@ -572,11 +572,16 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
     const char* v = getenv("HK_K1");
     variant = (v && v[0] == 'c') ? 1 : ((v && v[0] == 't' && v[1] == 'w') ? 2 : 0);
   }
-  if (variant == 1 && C == 512) {
+  // Under CUDA-graph capture the tile kernel's per-launch tag would be frozen into the graph and every replay would
+  // accept the previous replay's tile sums: captured launches take a route without cross-CTA state.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { (void)cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
+  if ((variant == 1 || capturing) && C == 512) {
     r = bcnn_cluster_fwd(tm, y, invn, B, HW, inv_hw, stream);
     if (r != HK_ERR_UNSUPPORTED) return r;
   }
-  if (variant != 2) {
+  if (variant != 2 && !capturing) {
     r = bcnn_tiles_fwd(tm, x, y, invn, B, C, HW, inv_hw, stream);
     if (r != HK_ERR_UNSUPPORTED) return r;        // more tiles per image than the slot table holds: two-kernel path
   }

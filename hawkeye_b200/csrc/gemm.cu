@@ -179,34 +179,77 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (row < M && col0 < N) {
+          // general epilogue: raw addend E, alpha, diagonal, beta*(D [+ D_lo]), ReLU / rounding, plain / (hi, lo) / transposed
+          // store.  A thread owns 32 consecutive columns of one row: whole aligned chunks move as float4 (the Newton-Schulz
+          // chain lives on this path; scalar accesses made its epilogues 3-8x longer than the MMAs)
+          const bool full = col0 + 32 <= N;
+          const float* ep = Eb ? Eb + (long long)row * ldE + col0 : nullptr;
+          const float* dp = Db ? Db + (long long)row * epi.ldd + col0 : nullptr;
+          const float* dlp = Dlb ? Dlb + (long long)row * epi.ldd + col0 : nullptr;
+          auto vec_ok = [&](const void* q) { return full && (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+          if (ep) {
+            if (vec_ok(ep)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(ep + j);
+                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < N) v[j] += ep[j];
+            }
+          }
+          float dv[32];
+          if (dp) {
+            if (vec_ok(dp) && (!dlp || vec_ok(dlp))) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 t = *reinterpret_cast<const float4*>(dp + j);
+                if (dlp) {
+                  const float4 u = *reinterpret_cast<const float4*>(dlp + j);
+                  t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                }
+                dv[j] = t.x; dv[j + 1] = t.y; dv[j + 2] = t.z; dv[j + 3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                dv[j] = 0.f;
+                if (col0 + j < N) dv[j] = dp[j] + (dlp ? dlp[j] : 0.f);
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            float acc = v[j];
-            if (Eb && col < N) acc += Eb[(long long)row * ldE + col];
-            float o = alpha * acc;
-            if (col == row) o += epi.diag;
-            if (Db && col < N) {
-              float dv = Db[(long long)row * epi.ldd + col];
-              if (Dlb) dv += Dlb[(long long)row * epi.ldd + col];
-              o += beta * dv;
-            }
+            float o = alpha * v[j];
+            if (col0 + j == row) o += epi.diag;
+            if (dp) o += beta * dv[j];
             if (epi.relu & 1) o = fmaxf(o, 0.f);
             if (epi.relu & 2) o = tf32_round(o);   // output feeds another tf32 MMA: keep its error unbiased
             v[j] = o;
           }
           if (Clb) {   // (hi, lo) split store; not combined with trans_c
+            float* hp = Cb + (long long)row * epi.ldc + col0;
+            float* lp = Clb + (long long)row * epi.ldc + col0;
+            if (vec_ok(hp) && vec_ok(lp)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float hi = tf32_round(v[j]);
-              if (col0 + j < N) {
-                Cb[(long long)row * epi.ldc + col0 + j] = hi;
-                Clb[(long long)row * epi.ldc + col0 + j] = tf32_round(v[j] - hi);
+              for (int j = 0; j < 32; j += 4) {
+                const float h0 = tf32_round(v[j]), h1 = tf32_round(v[j + 1]), h2 = tf32_round(v[j + 2]), h3 = tf32_round(v[j + 3]);
+                *reinterpret_cast<float4*>(hp + j) = make_float4(h0, h1, h2, h3);
+                *reinterpret_cast<float4*>(lp + j) = make_float4(tf32_round(v[j] - h0), tf32_round(v[j + 1] - h1),
+                                                                 tf32_round(v[j + 2] - h2), tf32_round(v[j + 3] - h3));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float hi = tf32_round(v[j]);
+                if (col0 + j < N) { hp[j] = hi; lp[j] = tf32_round(v[j] - hi); }
               }
             }
           } else if (!epi.trans_c) {
             float* dst = Cb + (long long)row * epi.ldc + col0;
-            if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            if (vec_ok(dst)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
                 *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);

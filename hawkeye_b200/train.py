@@ -214,16 +214,66 @@ class Trainer:
         cur.wait_event(ev)
         return slot['img'], slot['lab'], slot
 
+    # ---- CUDA-graph replay of forward + loss + backward (+ gradient all-reduce) ----------------------------------------
+    # A ResNet-50 step is ~1500 short launches issued from Python: the host, not the GPU, sets the step time.  With
+    # ``experiment.cuda_graph: true`` (or $HK_CUDA_GRAPH=1) the step is captured once — after three eager warm-up steps, for
+    # one batch shape — and replayed from a static input buffer; the optimizer stays outside the graph (its learning rate
+    # and Adam's bias corrections are launch arguments that change from step to step).
+    def _graph_wanted(self):
+        if getattr(self, '_graph_mode', None) is None:
+            env = os.environ.get('HK_CUDA_GRAPH')
+            exp = self.config.experiment
+            self._graph_mode = (env == '1') if env is not None else bool(exp.cuda_graph if 'cuda_graph' in exp else False)
+            self._graph, self._graph_steps = None, 0
+        return self._graph_mode
+
+    def _graph_step(self, images, labels):
+        """-> (outputs, loss) of this batch.  Eager for the first three calls, then capture, then replay."""
+        key = (tuple(images.shape), tuple(labels.shape))
+        if self._graph is not None and self._graph['key'] != key:
+            self._graph = None                                         # another batch shape (last batch of an epoch): eager
+            self._graph_steps = -1
+        if self._graph is None:
+            outputs = self.model(images)
+            loss = self.criterion(outputs, labels)
+            self.optimizer.zero_grad()
+            loss.backward()
+            self.allreduce.finish()
+            if self._graph_steps >= 0:
+                self._graph_steps += 1
+            if self._graph_steps == 3:
+                g = dict(key=key, img=torch.empty_like(images), lab=torch.empty_like(labels), graph=torch.cuda.CUDAGraph())
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g['graph']):
+                    g['out'] = self.model(g['img'])
+                    g['loss'] = self.criterion(g['out'], g['lab'])
+                    g['correct'] = getattr(self.criterion, 'last_correct', None)
+                    self.optimizer.zero_grad()
+                    g['loss'].backward()
+                    self.allreduce.finish()
+                self._graph = g
+            return outputs, loss
+        g = self._graph
+        g['img'].copy_(images, non_blocking=True)
+        g['lab'].copy_(labels, non_blocking=True)
+        g['graph'].replay()
+        if g['correct'] is not None:
+            self.criterion.last_correct = g['correct']
+        return g['out'], g['loss']
+
     def batch_training(self, data):
         """train.py:310-325: forward, CE(label_smoothing), zero_grad, backward, (grad all-reduce), step, meters.
         No host synchronisation: loss and top-1 count are copied back asynchronously every step (8 bytes into pinned
         memory) and folded into the meters when they have landed."""
         images, labels, slot = self.stage_inputs(data)
-        outputs = self.model(images)
-        loss = self.criterion(outputs, labels)
-        self.optimizer.zero_grad()
-        loss.backward()
-        self.allreduce.finish()
+        if self._graph_wanted():
+            outputs, loss = self._graph_step(images, labels)
+        else:
+            outputs = self.model(images)
+            loss = self.criterion(outputs, labels)
+            self.optimizer.zero_grad()
+            loss.backward()
+            self.allreduce.finish()
         self.optimizer.step()
         if slot is not None:                                          # the input slot may be overwritten from here on
             slot['free'] = torch.cuda.Event()

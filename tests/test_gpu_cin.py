@@ -40,12 +40,15 @@ def test_channel_interaction_module(tag, C, size, B, precise):
             'fc.weight': rel_l2(m.fc.weight.grad.cpu()[:, ::37], G[f'{tag}_g_fc.weight_slice']),
             'fc.bias': rel_l2(m.fc.bias.grad.cpu(), G[f'{tag}_g_fc.bias'])}
     print(tag, f'precise={precise}', {k: f'{v:.1e}' for k, v in errs.items()})
-    tol_f, tol_b = (1e-3, 3e-3) if not precise else (1e-4, 2e-4)
+    # TF32: three chained single-pass products (W.X, conv, fc-weighted W_CCI.X) + the conv's tf32 store; precise: 3xTF32
+    tol_f, tol_b = (3e-3, 5e-3) if not precise else (1e-4, 2e-4)
     assert max(errs['z'], errs['zcci'], errs['z_eval']) < tol_f
     assert max(errs[k] for k in ('dx', 'conv.weight', 'conv.bias', 'fc.weight', 'fc.bias')) < tol_b
 
 
-def test_cin_full_size_forward():
+@pytest.mark.parametrize('precise', [0, 1])
+def test_cin_full_size_forward(precise):
+    from hawkeye_b200 import _lib
     from hawkeye_b200.methods.cin import ChannelInteractionModule, CINClassifier
     m = ChannelInteractionModule(in_channel=2048, spatial_size=(14, 14))
     m.load_state_dict(detgen.state_like(m))
@@ -53,10 +56,16 @@ def test_cin_full_size_forward():
     cls.load_state_dict(detgen.state_like(cls))
     m, cls = m.cuda().eval(), cls.cuda().eval()
     x = detgen.det((2, 2048, 14, 14), 94, positive=True).cuda()
-    with torch.no_grad():
-        z = m(x)
-        logits = cls(z)
+    _lib.set_precise(precise)
+    try:
+        with torch.no_grad():
+            z = m(x)
+            logits = cls(z)
+    finally:
+        _lib.set_precise(0)
     z4 = z.view(2, 2048, 196)
-    assert rel_l2(z4.cpu()[:, ::64, ::7], G['full_z_slice']) < 1e-3
+    ez, el = rel_l2(z4.cpu()[:, ::64, ::7], G['full_z_slice']), rel_l2(logits.cpu(), G['full_logits'])
+    print(f'cin full size precise={precise}: z {ez:.2e} logits {el:.2e}')
+    tol = 3e-3 if not precise else 1e-4
+    assert ez < tol and el < tol
     assert abs(z.double().sum().item() - float(G['full_z_sum'])) / abs(float(G['full_z_sum'])) < 1e-3
-    assert rel_l2(logits.cpu(), G['full_logits']) < 1e-3
