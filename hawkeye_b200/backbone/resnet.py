@@ -60,6 +60,26 @@ class ResNetTrunk(nn.Sequential):
 
 
 @BACKBONE.register
+def resnet101(pretrained=False, progress=True, **kwargs):
+    """Reference signature (resnet.py:309-319); the trunk of OSMENet (OSME.py:55-56).  Offline => reference initialisers
+    unless $HAWKEYE_RESNET101_PTH points at torchvision's checkpoint."""
+    import os
+    import torch
+    trunk = ResNetTrunk((3, 4, 23, 3))
+    path = os.environ.get('HAWKEYE_RESNET101_PTH')
+    if pretrained and path and os.path.exists(path):
+        sd = torch.load(path, map_location='cpu')
+        names = ['conv1', 'bn1', 'relu', 'maxpool', 'layer1', 'layer2', 'layer3', 'layer4']
+        trunk.load_state_dict({str(names.index(k.split('.')[0])) + k[len(k.split('.')[0]):]: v for k, v in sd.items()
+                               if k.split('.')[0] in names})
+    elif pretrained and os.environ.get('HAWKEYE_ALLOW_RANDOM_INIT', '0') != '1':
+        import logging
+        logging.getLogger('hawkeye_b200').warning('resnet101(pretrained=True): no checkpoint at $HAWKEYE_RESNET101_PTH (%r) — the '
+                                                  'trunk keeps the reference\'s RANDOM initialisation', path)
+    return trunk
+
+
+@BACKBONE.register
 def resnet50(pretrained=False, progress=True, **kwargs):
     """Reference signature (resnet.py:296-306); offline => reference initialisers unless $HAWKEYE_RESNET50_PTH is set."""
     import os

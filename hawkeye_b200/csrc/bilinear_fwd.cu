@@ -330,15 +330,43 @@ void set_k1_trace(void* buf) { g_k1_trace = static_cast<unsigned long long*>(buf
 
 // x [B,512,HW] -> y [B,512*512]; returns 0, <0 (argument) or >0 (cudaError_t); HK_ERR_UNSUPPORTED if clusters of four
 // cannot be scheduled with this much shared memory (the caller then uses the two-kernel path).
-int bcnn_cluster_fwd(const CUtensorMap& tmX, float* y, float* inv_norm, int B, int HW, float inv_hw, cudaStream_t stream) {
-  static int max_clusters = -1;
-  static bool attr_set = false;
-  cudaError_t e;
-  if (!attr_set) {
-    e = cudaFuncSetAttribute(bcnn_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);
-    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(bcnn_cluster_fwd): %s", cudaGetErrorString(e));
-    attr_set = true;
+// one-time host-side setup (function attribute + cluster occupancy query).  Kept out of the launch path so that the
+// first launch may happen inside a CUDA-graph capture, where only stream work is legal.
+static int g_max_clusters = -1;
+int bcnn_cluster_prepare() {
+  if (g_max_clusters >= 0) return 0;
+  cudaError_t e = cudaFuncSetAttribute(bcnn_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);
+  if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(bcnn_cluster_fwd): %s", cudaGetErrorString(e));
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(CF_THREADS);
+  cfg.dynamicSmemBytes = CF_SMEM;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CF_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int sms = 148, dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cfg.gridDim = dim3((sms / CF_CLUSTER) * CF_CLUSTER);
+  e = cudaOccupancyMaxActiveClusters(&n, bcnn_cluster_fwd_kernel, &cfg);
+  if (e != cudaSuccess || n <= 0) {
+    (void)cudaGetLastError();
+    n = 0;
   }
+  if (const char* v = getenv("HK_K1_CLUSTERS")) { const int f = atoi(v); if (f > 0 && f < n) n = f; }
+  g_max_clusters = n;
+  return 0;
+}
+
+int bcnn_cluster_fwd(const CUtensorMap& tmX, float* y, float* inv_norm, int B, int HW, float inv_hw, cudaStream_t stream,
+                     bool allow_pdl) {
+  int r = bcnn_cluster_prepare();
+  if (r) return r;
+  const int max_clusters = g_max_clusters;
+  cudaError_t e;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(CF_THREADS);
   cfg.dynamicSmemBytes = CF_SMEM;
@@ -351,24 +379,10 @@ int bcnn_cluster_fwd(const CUtensorMap& tmX, float* y, float* inv_norm, int B, i
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  if (max_clusters < 0) {
-    int sms = 148, dev = 0, n = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cfg.gridDim = dim3((sms / CF_CLUSTER) * CF_CLUSTER);
-    cfg.numAttrs = 1;
-    e = cudaOccupancyMaxActiveClusters(&n, bcnn_cluster_fwd_kernel, &cfg);
-    if (e != cudaSuccess || n <= 0) {
-      (void)cudaGetLastError();
-      max_clusters = 0;
-    } else {
-      max_clusters = n;
-    }
-    if (const char* v = getenv("HK_K1_CLUSTERS")) { const int f = atoi(v); if (f > 0 && f < max_clusters) max_clusters = f; }
-  }
   if (max_clusters == 0) return set_error(HK_ERR_UNSUPPORTED, "bcnn_cluster_fwd: clusters of %d CTAs cannot be scheduled", CF_CLUSTER);
-  static int pdl = -1;
-  if (pdl < 0) { const char* v = getenv("HK_K1_PDL"); pdl = v ? atoi(v) : 1; }
+  static int pdl_env = -1;
+  if (pdl_env < 0) { const char* v = getenv("HK_K1_PDL"); pdl_env = v ? atoi(v) : 1; }
+  const int pdl = (pdl_env && allow_pdl) ? 1 : 0;
   CfArgs a = {};
   a.B = B; a.HW = HW; a.inv_hw = inv_hw; a.eps = 1e-5f; a.Y = y; a.inv_norm = inv_norm; a.pdl = pdl;
   { const char* v = getenv("HK_K1_DBG"); a.dbg = v ? atoi(v) : 0; }

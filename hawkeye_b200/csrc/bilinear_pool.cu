@@ -28,7 +28,9 @@
 
 namespace hk {
 
-int bcnn_cluster_fwd(const CUtensorMap& tmX, float* y, float* inv_norm, int B, int HW, float inv_hw, cudaStream_t stream);   // bilinear_fwd.cu
+int bcnn_cluster_fwd(const CUtensorMap& tmX, float* y, float* inv_norm, int B, int HW, float inv_hw, cudaStream_t stream,
+                     bool allow_pdl);                                                                          // bilinear_fwd.cu
+int bcnn_cluster_prepare();
 int bcnn_tiles_fwd(const CUtensorMap& tmX, const float* x, float* y, float* inv_norm, int B, int C, int HW, float inv_hw,
                    cudaStream_t stream);                                                                       // bilinear_fwd_tiles.cu
 
@@ -577,8 +579,9 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { (void)cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
   const bool capturing = cap != cudaStreamCaptureStatusNone;
+  if (!capturing && C == 512 && (r = bcnn_cluster_prepare())) return r;     // host-side setup never happens inside a capture
   if ((variant == 1 || capturing) && C == 512) {
-    r = bcnn_cluster_fwd(tm, y, invn, B, HW, inv_hw, stream);
+    r = bcnn_cluster_fwd(tm, y, invn, B, HW, inv_hw, stream, /*allow_pdl=*/!capturing);
     if (r != HK_ERR_UNSUPPORTED) return r;
   }
   if (variant != 2 && !capturing) {

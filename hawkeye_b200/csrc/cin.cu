@@ -118,6 +118,39 @@ __global__ void row_mean_bwd_kernel(const float* __restrict__ dy, float* __restr
   }
 }
 
+// OSME excitation (reference model/methods/OSME.py:8-24): s[n][c][p] = sigmoid(m[n][c]) * x[n][c][p]
+__global__ void se_gate_fwd_kernel(const float* __restrict__ x, const float* __restrict__ m, float* __restrict__ s,
+                                   size_t rows, int hw) {
+  const size_t total = rows * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const float g = 1.f / (1.f + expf(-m[i / hw]));
+    s[i] = g * x[i];
+  }
+}
+// dx = sigmoid(m) * ds ;  dm[n][c] = sigmoid'(m) * sum_p ds * x      (one warp per (n, c) row)
+__global__ void se_gate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ m, const float* __restrict__ ds,
+                                   float* __restrict__ dx, float* __restrict__ dm, long long rows, int hw) {
+  const long long r = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float g = 1.f / (1.f + expf(-m[r]));
+  float acc = 0.f;
+  for (int p = lane; p < hw; p += 32) {
+    const float d = ds[r * hw + p];
+    acc = fmaf(d, x[r * hw + p], acc);
+    dx[r * hw + p] = g * d;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) dm[r] = acc * g * (1.f - g);
+}
+__global__ void relu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = fmaxf(x[i], 0.f);
+}
+__global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
 static inline int cgrid(size_t n, int block) {
   size_t g = (n + block - 1) / block;
   const size_t cap = 148 * 16;
@@ -156,6 +189,31 @@ int hk_cci_weight_bwd(const float* w_sci, const float* weight, const float* d_cc
   if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(d_weight): %s", cudaGetErrorString(e));
   cci_weight_bwd_kernel<<<dim3(64, B), 256, 0, (cudaStream_t)stream>>>(w_sci, weight, d_cci, d_sci, d_weight, B, (size_t)per);
   HK_LAUNCH_CHECK("cci_weight_bwd_kernel");
+  return 0;
+}
+int hk_se_gate_fwd(const float* x, const float* m, float* s, long long rows, int hw, void* stream) {
+  HK_REQUIRE(x && m && s && rows > 0 && hw > 0, HK_ERR_ARG, "hk_se_gate_fwd: bad args");
+  se_gate_fwd_kernel<<<cgrid((size_t)rows * hw, 256), 256, 0, (cudaStream_t)stream>>>(x, m, s, (size_t)rows, hw);
+  HK_LAUNCH_CHECK("se_gate_fwd_kernel");
+  return 0;
+}
+int hk_se_gate_bwd(const float* x, const float* m, const float* ds, float* dx, float* dm, long long rows, int hw,
+                   void* stream) {
+  HK_REQUIRE(x && m && ds && dx && dm && rows > 0 && hw > 0, HK_ERR_ARG, "hk_se_gate_bwd: bad args");
+  se_gate_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, m, ds, dx, dm, rows, hw);
+  HK_LAUNCH_CHECK("se_gate_bwd_kernel");
+  return 0;
+}
+int hk_relu_fwd(const float* x, float* y, size_t n, void* stream) {
+  HK_REQUIRE(x && y, HK_ERR_ARG, "hk_relu_fwd: null pointer");
+  relu_fwd_kernel<<<cgrid(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  HK_LAUNCH_CHECK("relu_fwd_kernel");
+  return 0;
+}
+int hk_relu_bwd(const float* y, const float* dy, float* dx, size_t n, void* stream) {
+  HK_REQUIRE(y && dy && dx, HK_ERR_ARG, "hk_relu_bwd: null pointer");
+  relu_bwd_kernel<<<cgrid(n, 256), 256, 0, (cudaStream_t)stream>>>(y, dy, dx, n);
+  HK_LAUNCH_CHECK("relu_bwd_kernel");
   return 0;
 }
 int hk_row_mean_fwd(const float* x, float* y, long long rows, int cols, int ld, void* stream) {

@@ -120,6 +120,19 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// ToTensor + Normalize (dataset/transforms.py:14-19, test.py:80-85) on the GPU: uint8 HWC -> fp32 NCHW, (x/255 - mean)/std
+__global__ void normalize_u8_kernel(const unsigned char* __restrict__ x, float* __restrict__ y, size_t npix, size_t hw,
+                                    float m0, float m1, float m2, float i0, float i1, float i2) {
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = p / hw, q = p - n * hw;
+    const unsigned char* s = x + p * 3;
+    float* d = y + n * 3 * hw + q;
+    d[0] = ((float)s[0] * (1.f / 255.f) - m0) * i0;
+    d[hw] = ((float)s[1] * (1.f / 255.f) - m1) * i1;
+    d[2 * hw] = ((float)s[2] * (1.f / 255.f) - m2) * i2;
+  }
+}
+
 static inline int grid_for(size_t n, int block) {
   size_t g = (n + block - 1) / block;
   const size_t cap = 148 * 16;
@@ -192,6 +205,17 @@ int hk_softmax_ce_ls(const float* logits, const long long* labels, float* loss, 
   softmax_ce_ls_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, labels, loss, dlogits, correct, B, K,
                                                            label_smoothing, grad_scale, precise() ? 0 : 1);
   HK_LAUNCH_CHECK("softmax_ce_ls_kernel");
+  return 0;
+}
+
+int hk_normalize_u8(const unsigned char* x_nhwc, float* y_nchw, int N, int H, int W, float mean0, float mean1, float mean2,
+                    float std0, float std1, float std2, void* stream) {
+  HK_REQUIRE(x_nhwc && y_nchw && N > 0 && H > 0 && W > 0, HK_ERR_ARG, "hk_normalize_u8: bad args");
+  HK_REQUIRE(std0 > 0.f && std1 > 0.f && std2 > 0.f, HK_ERR_ARG, "hk_normalize_u8: std must be positive");
+  const size_t hw = (size_t)H * W, npix = hw * N;
+  normalize_u8_kernel<<<grid_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(x_nhwc, y_nchw, npix, hw, mean0, mean1, mean2,
+                                                                            1.f / std0, 1.f / std1, 1.f / std2);
+  HK_LAUNCH_CHECK("normalize_u8_kernel");
   return 0;
 }
 

@@ -192,3 +192,44 @@ class AddFn(Function):
     @staticmethod
     def backward(ctx, g):
         return g, g
+
+
+class SEGateFn(Function):
+    """sigmoid(m)[n, c] * x[n, c, :, :]  (OSME.py:19-23)"""
+
+    @staticmethod
+    def forward(ctx, x, m):
+        _check_cuda(x, m)
+        x, m = _f32c(x), _f32c(m)
+        N, C = x.shape[:2]
+        hw = x.numel() // (N * C)
+        s = torch.empty_like(x)
+        _lib.call('hk_se_gate_fwd', x, m, s, N * C, hw, _lib.stream_ptr())
+        ctx.save_for_backward(x, m)
+        return s
+
+    @staticmethod
+    def backward(ctx, ds):
+        x, m = ctx.saved_tensors
+        N, C = x.shape[:2]
+        hw = x.numel() // (N * C)
+        dx, dm = torch.empty_like(x), torch.empty_like(m)
+        _lib.call('hk_se_gate_bwd', x, m, _f32c(ds), dx, dm, N * C, hw, _lib.stream_ptr())
+        return dx, dm
+
+
+class ReluFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32c(x)
+        y = torch.empty_like(x)
+        _lib.call('hk_relu_fwd', x, y, x.numel(), _lib.stream_ptr())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dx = torch.empty_like(y)
+        _lib.call('hk_relu_bwd', y, _f32c(dy), dx, y.numel(), _lib.stream_ptr())
+        return dx

@@ -228,7 +228,21 @@ class Trainer:
         return self._graph_mode
 
     def _graph_step(self, images, labels):
-        """-> (outputs, loss) of this batch.  Eager for the first three calls, then capture, then replay."""
+        """-> (outputs, loss) of this batch.  Eager for the first three calls, then capture, then replay.
+
+        Everything — warm-up steps included — runs on ONE dedicated non-default stream: autograd binds each parameter's
+        AccumulateGrad node to the stream of its first use, and a node bound to the legacy default stream cannot be joined from
+        a capturing stream.  The caller's stream is ordered before and after (wait_stream), so callers see no difference."""
+        if getattr(self, '_graph_stream', None) is None:
+            self._graph_stream = torch.cuda.Stream(device=self.device)
+        cur, gs = torch.cuda.current_stream(), self._graph_stream
+        gs.wait_stream(cur)
+        with torch.cuda.stream(gs):
+            out = self._graph_step_on_stream(images, labels, gs)
+        cur.wait_stream(gs)
+        return out
+
+    def _graph_step_on_stream(self, images, labels, gs):
         key = (tuple(images.shape), tuple(labels.shape))
         if self._graph is not None and self._graph['key'] != key:
             self._graph = None                                         # another batch shape (last batch of an epoch): eager
@@ -243,8 +257,8 @@ class Trainer:
                 self._graph_steps += 1
             if self._graph_steps == 3:
                 g = dict(key=key, img=torch.empty_like(images), lab=torch.empty_like(labels), graph=torch.cuda.CUDAGraph())
-                torch.cuda.synchronize()
-                with torch.cuda.graph(g['graph']):
+                gs.synchronize()
+                with torch.cuda.graph(g['graph'], stream=gs):
                     g['out'] = self.model(g['img'])
                     g['loss'] = self.criterion(g['out'], g['lab'])
                     g['correct'] = getattr(self.criterion, 'last_correct', None)

@@ -185,6 +185,14 @@ int hk_cci_weight_bwd(const float* w_sci, const float* weight, const float* d_cc
 int hk_row_mean_fwd(const float* x, float* y, long long rows, int cols, int ld, void* stream);
 int hk_row_mean_bwd(const float* dy, float* dx, long long rows, int cols, int ld, void* stream);
 
+/* ---- OSME excitation (model/methods/OSME.py:8-24): s = sigmoid(m)[n,c] * x[n,c,:] and its backward; the
+ * squeeze (AdaptiveAvgPool2d) is hk_row_mean_*, the two Linear layers are hk_linear_*, ReLU on the bottleneck hk_relu_* */
+int hk_se_gate_fwd(const float* x, const float* m, float* s, long long rows, int hw, void* stream);
+int hk_se_gate_bwd(const float* x, const float* m, const float* ds, float* dx, float* dm, long long rows, int hw,
+                   void* stream);
+int hk_relu_fwd(const float* x, float* y, size_t n, void* stream);
+int hk_relu_bwd(const float* y, const float* dy, float* dx, size_t n, void* stream);
+
 /* ---- classifier nn.Linear (BCNN.py:42, CBCNN.py:26, MPNCOV.py:31) as skinny tcgen05 GEMMs ------------------- */
 size_t hk_linear_fwd_workspace_bytes(int B, int F, int N);
 int hk_linear_fwd(const float* x, const float* w, const float* bias, float* y, int B, int F, int N, void* workspace,
@@ -198,6 +206,11 @@ int hk_linear_wgrad(const float* dy, const float* x, float* dw, float* db, int B
  * MMAs, which would otherwise truncate it); hk_set_precise(1) stores it unrounded. */
 int hk_softmax_ce_ls(const float* logits, const long long* labels, float* loss, float* dlogits, int* correct, int B,
                      int K, float label_smoothing, float grad_scale, void* stream);
+
+/* ---- input side: transforms.ToTensor + Normalize (dataset/transforms.py:14-19, test.py:80-85) fused on
+ * the GPU: uint8 HWC batch [N,H,W,3] -> fp32 NCHW (x/255 - mean_c)/std_c; a quarter of the float pipeline's H2D bytes */
+int hk_normalize_u8(const unsigned char* x_nhwc, float* y_nchw, int N, int H, int W, float mean0, float mean1, float mean2,
+                    float std0, float std1, float std2, void* stream);
 
 /* ---- optimizers over flat fp32 buffers: torch.optim.SGD (Examples/BCNN.py:40), Adam (Examples/MPN.py:14-18) */
 int hk_sgd_momentum(float* p, const float* g, float* buf, size_t n, float lr, float momentum, float weight_decay,

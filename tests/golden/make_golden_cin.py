@@ -58,3 +58,23 @@ net = MODEL.get('CIN')(rh.cfg(name='CIN', num_classes=200))
 out['cin_state_keys_json'] = np.frombuffer(json.dumps({k: list(v.shape) for k, v in net.state_dict().items()}, sort_keys=True).encode(), dtype=np.uint8)
 np.savez_compressed(os.path.join(HERE, 'reference_cin.npz'), **out)
 print('wrote', len(out), 'arrays;', os.path.getsize(os.path.join(HERE, 'reference_cin.npz')) / 1e6, 'MB')
+
+# ---- OSME (model/methods/OSME.py:8-64): the excitation module on its own + the OSMENet key list -----------
+from model.methods.OSME import OSME  # noqa: E402
+
+for tag, C, shape, B in (('osme_c256_7', 256, 7, 4), ('osme_c128_14', 128, (14, 14), 2)):
+    m = OSME(C, 64, feature_shape=shape, num_attention=2)
+    m.load_state_dict(detgen.state_like(m))
+    hw = shape if isinstance(shape, tuple) else (shape, shape)
+    x = detgen.det((B, C, hw[0], hw[1]), 95, positive=True).requires_grad_(True)
+    f, parts = m(x)
+    r1, r2 = detgen.det(f.shape, 96), detgen.det(parts.shape, 97)
+    ((f * r1).sum() + (parts * r2).sum()).backward()
+    out[f'{tag}_f'], out[f'{tag}_parts'], out[f'{tag}_dx'] = f.detach().numpy(), parts.detach().numpy(), x.grad.numpy()
+    for k, p in m.named_parameters():
+        g = p.grad.numpy()
+        out[f'{tag}_g_{k}'] = g if g.size <= 65536 else g.reshape(g.shape[0], -1)[:, ::29]
+net = MODEL.get('OSMENet')(rh.cfg(name='OSMENet', num_attention=2, num_classes=200))
+out['osme_state_keys_json'] = np.frombuffer(json.dumps({k: list(v.shape) for k, v in net.state_dict().items()}, sort_keys=True).encode(), dtype=np.uint8)
+np.savez_compressed(os.path.join(HERE, 'reference_cin.npz'), **out)
+print('wrote', len(out), 'arrays (with OSME);', os.path.getsize(os.path.join(HERE, 'reference_cin.npz')) / 1e6, 'MB')

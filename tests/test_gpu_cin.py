@@ -69,3 +69,31 @@ def test_cin_full_size_forward(precise):
     tol = 3e-3 if not precise else 1e-4
     assert ez < tol and el < tol
     assert abs(z.double().sum().item() - float(G['full_z_sum'])) / abs(float(G['full_z_sum'])) < 1e-3
+
+
+@pytest.mark.parametrize('precise', [0, 1])
+@pytest.mark.parametrize('tag,C,shape,B', [('osme_c256_7', 256, 7, 4), ('osme_c128_14', 128, (14, 14), 2)])
+def test_osme_module(tag, C, shape, B, precise):
+    """OSME (OSME.py:8-46) against the reference: summed / per-attention features, input and all parameter grads."""
+    from hawkeye_b200 import _lib
+    from hawkeye_b200.methods.osme import OSME
+    m = OSME(C, 64, feature_shape=shape, num_attention=2)
+    m.load_state_dict(detgen.state_like(m))
+    m = m.cuda().train()
+    hw = shape if isinstance(shape, tuple) else (shape, shape)
+    x = detgen.det((B, C, hw[0], hw[1]), 95, positive=True).cuda().requires_grad_(True)
+    _lib.set_precise(precise)
+    try:
+        f, parts = m(x)
+        ((f * detgen.det(f.shape, 96).cuda()).sum() + (parts * detgen.det(parts.shape, 97).cuda()).sum()).backward()
+    finally:
+        _lib.set_precise(0)
+    errs = {'f': rel_l2(f.detach().cpu(), G[f'{tag}_f']), 'parts': rel_l2(parts.detach().cpu(), G[f'{tag}_parts']),
+            'dx': rel_l2(x.grad.cpu(), G[f'{tag}_dx'])}
+    for k, p in m.named_parameters():
+        g = p.grad.cpu()
+        g = g if g.numel() <= 65536 else g.reshape(g.shape[0], -1)[:, ::29]
+        errs[k] = rel_l2(g, G[f'{tag}_g_{k}'])
+    worst = max(errs, key=errs.get)
+    print(tag, f'precise={precise}', {k: f'{v:.1e}' for k, v in errs.items() if k in ('f', 'parts', 'dx', worst)})
+    assert errs[worst] < (3e-3 if not precise else 1e-4)
