@@ -464,6 +464,8 @@ def main():
     _lib.reset_launch_count()
     ms = timed(step_resident, args.steps)
     launches = _lib.launch_count()
+    if use_graph and getattr(tr, '_graph', None) is not None:       # replayed kernels are not seen by the host-side counter
+        launches += args.steps * tr._graph['kernels']
     clocks = sampler.stop() if rank == 0 else None
     value = B * world * args.steps / (ms * 1e-3)
 

@@ -258,6 +258,8 @@ class Trainer:
             if self._graph_steps == 3:
                 g = dict(key=key, img=torch.empty_like(images), lab=torch.empty_like(labels), graph=torch.cuda.CUDAGraph())
                 gs.synchronize()
+                from . import _lib
+                n0 = _lib.launch_count()
                 with torch.cuda.graph(g['graph'], stream=gs):
                     g['out'] = self.model(g['img'])
                     g['loss'] = self.criterion(g['out'], g['lab'])
@@ -265,6 +267,7 @@ class Trainer:
                     self.optimizer.zero_grad()
                     g['loss'].backward()
                     self.allreduce.finish()
+                g['kernels'] = _lib.launch_count() - n0        # library kernels recorded in the graph (replayed every step)
                 self._graph = g
             return outputs, loss
         g = self._graph

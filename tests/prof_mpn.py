@@ -1,6 +1,7 @@
-"""Profiling driver: 2 MPN (ResNet-50 + MPN-COV) train steps at 448x448, batch 32."""
+"""Profiling driver: 2 MPN (ResNet-50 + MPN-COV) train steps at 448x448, batch 32 (eager launches)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault('HAWKEYE_ALLOW_RANDOM_INIT', '1')
 import torch
 import hawkeye_b200 as hb
 from hawkeye_b200 import engine, ops
