@@ -33,6 +33,8 @@ int bcnn_cluster_fwd(const CUtensorMap& tmX, float* y, float* inv_norm, int B, i
 int bcnn_cluster_prepare();
 int bcnn_tiles_fwd(const CUtensorMap& tmX, const float* x, float* y, float* inv_norm, int B, int C, int HW, float inv_hw,
                    cudaStream_t stream);                                                                       // bilinear_fwd_tiles.cu
+int bcnn_super_fwd(const float* x, float* y, float* inv_norm, int B, int C, int HW, float inv_hw, cudaStream_t stream);  // bilinear_fwd_super.cu
+bool bcnn_super_one_wave(int B);      // B images fit in one wave of 4-CTA clusters
 
 __device__ __forceinline__ float fast_sqrt(float x) {
   float r;
@@ -567,12 +569,15 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
   }
   CUtensorMap tm;
   if ((r = make_x_map(&tm, x, B, C, HW))) return r;
-  // $HK_K1: "tiles" (default) = persistent 128x128-tile kernel, bounded-wait norm exchange (bilinear_fwd_tiles.cu);
+  // $HK_K1: unset = "super" while the batch is one wave of 4-CTA clusters (B <= ~33: the per-GPU batch of the train step),
+  //         "tiles" beyond (measured equal or better there);
+  //         "super" = super-tile kernel, four operand-sharing items per image, cluster / DSMEM norm exchange
+  //         (bilinear_fwd_super.cu); "tiles" = persistent 128x128-tile kernel, bounded-wait exchange (bilinear_fwd_tiles.cu);
   //         "cluster" = 4-CTA clusters, X multicast, no exchange at all (bilinear_fwd.cu; C = 512); "two" = pre-kernel + pairs
   static int variant = -1;
   if (variant < 0) {
     const char* v = getenv("HK_K1");
-    variant = (v && v[0] == 'c') ? 1 : ((v && v[0] == 't' && v[1] == 'w') ? 2 : 0);
+    variant = (v && v[0] == 'c') ? 1 : ((v && v[0] == 't' && v[1] == 'w') ? 2 : ((v && v[0] == 't') ? 0 : ((v && v[0] == 's') ? 3 : 4)));
   }
   // Under CUDA-graph capture the tile kernel's per-launch tag would be frozen into the graph and every replay would
   // accept the previous replay's tile sums: captured launches take a route without cross-CTA state.
@@ -582,6 +587,10 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
   if (!capturing && C == 512 && (r = bcnn_cluster_prepare())) return r;     // host-side setup never happens inside a capture
   if ((variant == 1 || capturing) && C == 512) {
     r = bcnn_cluster_fwd(tm, y, invn, B, HW, inv_hw, stream, /*allow_pdl=*/!capturing);
+    if (r != HK_ERR_UNSUPPORTED) return r;
+  }
+  if (!capturing && C == 512 && (variant == 3 || (variant == 4 && bcnn_super_one_wave(B)))) {
+    r = bcnn_super_fwd(x, y, invn, B, C, HW, inv_hw, stream);
     if (r != HK_ERR_UNSUPPORTED) return r;
   }
   if (variant != 2 && !capturing) {

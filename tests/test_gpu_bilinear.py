@@ -66,11 +66,15 @@ def test_full_batch_properties():
         ops.bilinear_pool(torch.rand(1, 100, 4, 4, device='cuda'))
 
 
-@pytest.mark.parametrize('env', [{'HK_K1_POLL_LIMIT': '0'}, {'HK_K1': 'cluster'}, {'HK_K1': 'two'}])
+@pytest.mark.parametrize('env', [{'HK_K1': 'tiles', 'HK_K1_POLL_LIMIT': '0'}, {'HK_K1': 'tiles'}, {'HK_K1': 'cluster'}, {'HK_K1': 'two'},
+                                 {'HK_K1': 'super'}, {'HK_K1': 'super', 'HK_K1_SUPER_CL': '0'},
+                                 {'HK_K1': 'super', 'HK_K1_SUPER_CL': '0', 'HK_K1_POLL_LIMIT': '0'}])
 def test_k1_variants_and_bounded_wait(env):
     """hk_bilinear_pool_fwd must be correct on every route: with the cross-CTA norm exchange of the tile kernel never
     succeeding (HK_K1_POLL_LIMIT=0: each CTA computes the norm itself — the path taken when peers are not co-resident),
-    on the 4-CTA cluster kernel, and on the two-kernel path.  The knobs are read once per process => subprocesses."""
+    on the 4-CTA cluster kernel, on the two-kernel path, and on the super-tile kernel with its cluster (DSMEM) and its
+    global-memory norm exchange (the default route picks super-tile clusters for B <= one wave, tiles beyond; the loop below
+    crosses that boundary).  The knobs are read once per process => subprocesses."""
     import os
     import subprocess
     import sys
