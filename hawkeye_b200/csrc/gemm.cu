@@ -32,15 +32,20 @@ struct GemmCfg {
 // boundaries: the epilogue of tile i overlaps the TMA/MMA of tile i+1.
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpi epi, int M,
-                 int N, int K, int a_mn, int b_mn, int shareA, int shareB, int mn_sbo, int mn_type, int nstages,
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmBl, int triple, GemmEpi epi,
+                 int M, int N, int K, int a_mn, int b_mn, int shareA, int shareB, int mn_sbo, int mn_type, int nstages,
                  int tiles_m, int tiles_n, int total_tiles) {
+  // triple: operands are (hi, lo) tf32 pairs (tmA/tmB = hi, tmAl/tmBl = lo) and every k-step issues Ah.Bl, Al.Bh, Ah.Bh
+  // into the same accumulator — the 3xTF32 product of the Newton-Schulz chain in ONE launch, no partial sums through memory
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + nstages * Cfg::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + nstages * Cfg::STAGE_BYTES);
+  uint8_t* sAl = smem + nstages * Cfg::STAGE_BYTES;
+  uint8_t* sBl = sAl + nstages * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + nstages * Cfg::STAGE_BYTES * (triple ? 2 : 1));
   uint64_t* empty = full + nstages;
   uint64_t* acc_full = empty + nstages;
   uint64_t* acc_empty = acc_full + 2;
@@ -82,9 +87,25 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int s = kbg % nstages;
           const uint32_t ph = (kbg / nstages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES * (triple ? 2 : 1));
           uint8_t* a = sA + s * Cfg::A_BYTES;
           uint8_t* b = sB + s * Cfg::B_BYTES;
+          if (triple) {
+            uint8_t* al = sAl + s * Cfg::A_BYTES;
+            uint8_t* bl = sBl + s * Cfg::B_BYTES;
+            if (!a_mn) {
+              tma_load_3d(al, &tmAl, &full[s], kb * 32, m0, bza);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) tma_load_3d(al + j * 4096, &tmAl, &full[s], m0 + j * 32, kb * 32, bza);
+            }
+            if (!b_mn) {
+              tma_load_3d(bl, &tmBl, &full[s], kb * 32, n0, bzb);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 32; ++j) tma_load_3d(bl + j * 4096, &tmBl, &full[s], n0 + j * 32, kb * 32, bzb);
+            }
+          }
           if (!a_mn) {
             tma_load_3d(a, &tmA, &full[s], kb * 32, m0, bza);
           } else {
@@ -123,8 +144,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int krem = K - kb * 32;
           const int ksteps = krem >= 32 ? 4 : (krem + 7) / 8;
           if (elect_one()) {
-            for (int ks = 0; ks < ksteps; ++ks)
-              umma_tf32_ss(d, a_base + ks * a_step, b_base + ks * b_step, idesc, (kb | ks) ? 1u : 0u);
+            if (triple) {
+              const uint64_t al_base = a_tmpl + (smem_u32(sAl + s * Cfg::A_BYTES) >> 4);
+              const uint64_t bl_base = b_tmpl + (smem_u32(sBl + s * Cfg::B_BYTES) >> 4);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                umma_tf32_ss(d, a_base + ks * a_step, bl_base + ks * b_step, idesc, (kb | ks) ? 1u : 0u);
+                umma_tf32_ss(d, al_base + ks * a_step, b_base + ks * b_step, idesc, 1u);
+                umma_tf32_ss(d, a_base + ks * a_step, b_base + ks * b_step, idesc, 1u);
+              }
+            } else {
+              for (int ks = 0; ks < ksteps; ++ks)
+                umma_tf32_ss(d, a_base + ks * a_step, b_base + ks * b_step, idesc, (kb | ks) ? 1u : 0u);
+            }
             umma_commit(&empty[s]);
           }
           __syncwarp();
@@ -301,7 +332,8 @@ static int dbg_env(const char* name, int dflt) {
 
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi& epi, int M, int N, int K,
-                       int batch, int a_mn, int b_mn, int shareA, int shareB, cudaStream_t stream) {
+                       int batch, int a_mn, int b_mn, int shareA, int shareB, cudaStream_t stream,
+                       const CUtensorMap* tmAl = nullptr, const CUtensorMap* tmBl = nullptr) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -320,10 +352,13 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int nk = (K + 31) / 32;
   const long long kblocks_per_cta = (long long)nk * ((total + sms - 1) / sms);
-  const int nstages = kblocks_per_cta < Cfg::STAGES ? (int)kblocks_per_cta : Cfg::STAGES;
-  const int smem = nstages * Cfg::STAGE_BYTES + 1024 + 256;
+  const int triple = tmAl ? 1 : 0;
+  const int max_stages = triple ? Cfg::STAGES / 2 : Cfg::STAGES;
+  const int nstages = kblocks_per_cta < max_stages ? (int)kblocks_per_cta : max_stages;
+  const int smem = nstages * Cfg::STAGE_BYTES * (triple ? 2 : 1) + 1024 + 256;
   const int grid = total < sms ? (int)total : sms;
-  umma_gemm_kernel<BN><<<grid, 192, smem, stream>>>(tmA, tmB, epi, M, N, K, a_mn, b_mn, shareA, shareB,
+  umma_gemm_kernel<BN><<<grid, 192, smem, stream>>>(tmA, tmB, triple ? *tmAl : tmA, triple ? *tmBl : tmB, triple, epi, M, N, K,
+                                                    a_mn, b_mn, shareA, shareB,
                                                     dbg_env("HK_DBG_MN_SBO", 512), dbg_env("HK_DBG_MN_TYPE", 1), nstages,
                                                     tiles_m, tiles_n, (int)total);
   HK_LAUNCH_CHECK("umma_gemm_kernel");
@@ -362,23 +397,15 @@ int gemm_tf32_3x(const float* A, int a_mn, long long lda, long long strideA, con
   const size_t nB = same ? 0 : operand_extent(b_mn ? K : N, b_mn ? N : K, ldb, strideB, batch);
   const size_t nA4 = (nA + 3) & ~size_t(3), nB4 = (nB + 3) & ~size_t(3);     // the lo halves start 16-byte aligned (TMA)
   Scratch sa(2 * nA4 * sizeof(float), st), sb(2 * (nB4 ? nB4 : 4) * sizeof(float), st);
-  Scratch tmp((size_t)batch * M * N * sizeof(float), st);
-  HK_REQUIRE(sa.p && sb.p && tmp.p, HK_ERR_DRIVER, "gemm (precise): cudaMallocAsync of the operand halves failed");
+  HK_REQUIRE(sa.p && sb.p, HK_ERR_DRIVER, "gemm (precise): cudaMallocAsync of the operand halves failed");
   float *Ah = sa.f(), *Al = Ah + nA4;
   float *Bh = same ? Ah : sb.f(), *Bl = same ? Al : Bh + nB4;
   int r;
   if ((r = tf32_split(A, Ah, Al, nA, st))) return r;
   if (!same && (r = tf32_split(B, Bh, Bl, nB, st))) return r;
-  GemmEpi e = {};
-  e.C = tmp.f(); e.ldc = N; e.strideC = (long long)M * N; e.alpha = 1.f;
-  e.E = epi.E; e.ldE = epi.E ? (epi.ldE ? epi.ldE : epi.ldc) : 0; e.strideE = epi.E ? (epi.ldE ? epi.strideE : epi.strideC) : 0;
-  if ((r = gemm_tf32_1x(Ah, a_mn, lda, strideA, Bl, b_mn, ldb, strideB, e, M, N, K, batch, st))) return r;   // tmp = Ah.Bl (+E)
-  e.E = tmp.f(); e.ldE = N; e.strideE = (long long)M * N;
-  if ((r = gemm_tf32_1x(Al, a_mn, lda, strideA, Bh, b_mn, ldb, strideB, e, M, N, K, batch, st))) return r;   // tmp += Al.Bh
   GemmEpi f = epi;
-  f.E = tmp.f(); f.ldE = N; f.strideE = (long long)M * N;
   f.relu &= ~2;                                                                                             // no rounding
-  return gemm_tf32_1x(Ah, a_mn, lda, strideA, Bh, b_mn, ldb, strideB, f, M, N, K, batch, st);
+  return gemm_tf32_pair(Ah, Al, a_mn, lda, strideA, Bh, Bl, b_mn, ldb, strideB, f, M, N, K, batch, st);     // one launch
 }
 
 int gemm_tf32(const float* A, int a_mn, long long lda, long long strideA, const float* B, int b_mn, long long ldb,
@@ -404,6 +431,33 @@ int gemm_tf32_1x(const float* A, int a_mn, long long lda, long long strideA, con
   if (BN == 64) return launch_gemm<64>(tmA, tmB, epi, M, N, K, batch, a_mn, b_mn, shareA, shareB, stream);
   if (BN == 128) return launch_gemm<128>(tmA, tmB, epi, M, N, K, batch, a_mn, b_mn, shareA, shareB, stream);
   return launch_gemm<256>(tmA, tmB, epi, M, N, K, batch, a_mn, b_mn, shareA, shareB, stream);
+}
+
+// C = epilogue(Ah.Bh + Al.Bh + Ah.Bl) in ONE launch; (Ah, Al) / (Bh, Bl) are tf32 (hi, lo) pairs with identical layouts.
+int gemm_tf32_pair(const float* Ah, const float* Al, int a_mn, long long lda, long long strideA, const float* Bh,
+                   const float* Bl, int b_mn, long long ldb, long long strideB, const GemmEpi& epi, int M, int N, int K,
+                   int batch, cudaStream_t stream) {
+  HK_REQUIRE(Ah && Al && Bh && Bl && epi.C, HK_ERR_ARG, "gemm_pair: null pointer");
+  HK_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0 && batch <= 65535, HK_ERR_ARG, "gemm_pair: bad shape M=%d N=%d K=%d batch=%d",
+             M, N, K, batch);
+  CUtensorMap tmA, tmB, tmAl, tmBl;
+  int shareA, shareB, r;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  // 128-wide tiles while 256-wide ones would leave SMs idle (Newton-Schulz: n = 256, batch 32 -> 128 tiles instead of 64)
+  int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  if (BN == 256 && (long long)((M + 127) / 128) * ((N + 255) / 256) * batch < sms) BN = 128;
+  if ((r = make_operand_map(&tmA, Ah, a_mn, lda, strideA, M, K, batch, 128, &shareA))) return r;
+  if ((r = make_operand_map(&tmAl, Al, a_mn, lda, strideA, M, K, batch, 128, &shareA))) return r;
+  if ((r = make_operand_map(&tmB, Bh, b_mn, ldb, strideB, N, K, batch, BN, &shareB))) return r;
+  if ((r = make_operand_map(&tmBl, Bl, b_mn, ldb, strideB, N, K, batch, BN, &shareB))) return r;
+  if (BN == 64) return launch_gemm<64>(tmA, tmB, epi, M, N, K, batch, a_mn, b_mn, shareA, shareB, stream, &tmAl, &tmBl);
+  if (BN == 128) return launch_gemm<128>(tmA, tmB, epi, M, N, K, batch, a_mn, b_mn, shareA, shareB, stream, &tmAl, &tmBl);
+  return launch_gemm<256>(tmA, tmB, epi, M, N, K, batch, a_mn, b_mn, shareA, shareB, stream, &tmAl, &tmBl);
 }
 
 }  // namespace hk

@@ -28,4 +28,9 @@ int gemm_tf32(const float* A, int a_mn, long long lda, long long strideA, const 
 int gemm_tf32_1x(const float* A, int a_mn, long long lda, long long strideA, const float* B, int b_mn, long long ldb,
                  long long strideB, const GemmEpi& epi, int M, int N, int K, int batch, cudaStream_t stream);
 
+// One launch of the 3xTF32 product for operands already held as tf32 (hi, lo) pairs:  C = epilogue(Ah.Bh + Al.Bh + Ah.Bl).
+int gemm_tf32_pair(const float* Ah, const float* Al, int a_mn, long long lda, long long strideA, const float* Bh,
+                   const float* Bl, int b_mn, long long ldb, long long strideB, const GemmEpi& epi, int M, int N, int K,
+                   int batch, cudaStream_t stream);
+
 }  // namespace hk

@@ -25,17 +25,13 @@ static inline int grid_for(size_t n, int block) {
 static int mm3(Pair A, Pair B, Pair C, float* tmp, int n, int batch, float alpha, const float* alpha_vec, float diag,
                const Pair* D, float beta, cudaStream_t st) {
   const long long s = (long long)n * n;
-  GemmEpi e = {};
-  e.C = tmp; e.ldc = n; e.strideC = s; e.alpha = 1.f;
-  int r = gemm_tf32_1x(A.hi, 0, n, s, B.lo, 1, n, s, e, n, n, n, batch, st);           // tmp  = Ah.Bl
-  if (r) return r;
-  e.E = tmp;
-  if ((r = gemm_tf32_1x(A.lo, 0, n, s, B.hi, 1, n, s, e, n, n, n, batch, st))) return r;  // tmp += Al.Bh  (E aliases C: each
-  GemmEpi f = {};                                                                     //  element read then written by one thread)
-  f.C = C.hi; f.C_lo = C.lo; f.ldc = n; f.strideC = s; f.E = tmp;
+  (void)tmp;
+  GemmEpi f = {};
+  f.C = C.hi; f.C_lo = C.lo; f.ldc = n; f.strideC = s;
   f.alpha = alpha; f.alpha_vec = alpha_vec; f.diag = diag;
   if (D) { f.D = D->hi; f.D_lo = D->lo; f.ldd = n; f.strideD = s; f.beta = beta; }
-  return gemm_tf32_1x(A.hi, 0, n, s, B.hi, 1, n, s, f, n, n, n, batch, st);            // C = alpha*(Ah.Bh + tmp) + ...
+  // one launch: every k-step issues Ah.Bl, Al.Bh, Ah.Bh into the same TMEM accumulator (gemm.cu, triple mode)
+  return gemm_tf32_pair(A.hi, A.lo, 0, n, s, B.hi, B.lo, 1, n, s, f, n, n, n, batch, st);
 }
 
 // ------------------------------------------------------------------------------------------------ small kernels
