@@ -24,7 +24,8 @@ struct GemmCfg {
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_TILE = 4 * 32 * 36 * 4;   // four epilogue warps x a 32 x 36-float transpose tile (coalesced row-major stores)
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_TILE;
 };
 
 // Persistent: one CTA per SM walks output tiles t, t+grid, ... (n-tile fastest, so CTAs running at the same time share
@@ -50,6 +51,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* acc_full = empty + nstages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* epi_tiles = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = (K + 31) / 32;
@@ -193,21 +195,32 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int col0 = n0 + c * 32;
         // fast path (plain scaled store of a full, aligned 32-column chunk): a handful of instructions per element — the
         // general path below costs ~60 and dominates short-K GEMMs such as the first VGG layer (K = 32)
-        if (simple && row < M && col0 + 32 <= N) {
-          float* dst = Cb + (long long)row * epi.ldc + col0;
-          if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        if (simple && col0 + 32 <= N && (epi.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cb) & 15) == 0) {
+          // A thread owns 32 consecutive columns of ONE row, so a direct float4 store instruction would touch 32 rows x 16 B —
+          // half-written 32 B sectors, twice the L2 write transactions (the 1x1-conv GEMMs of the ResNet trunk are
+          // output-write-bound).  Transpose the 32 x 32 chunk through a warp-private shared-memory tile instead: every store
+          // instruction then writes four full 128 B rows.
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float o = alpha * v[j];
-              if (epi.relu & 1) o = fmaxf(o, 0.f);
-              if (epi.relu & 2) o = tf32_round(o);
-              v[j] = o;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            continue;
+          for (int j = 0; j < 32; ++j) {
+            float o = alpha * v[j];
+            if (epi.relu & 1) o = fmaxf(o, 0.f);
+            if (epi.relu & 2) o = tf32_round(o);
+            v[j] = o;
           }
+          float* tile = epi_tiles + (warp - 2) * (32 * 36);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(tile + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          __syncwarp();
+          const int row0 = m0 + q * 32;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + (lane >> 3);
+            const float4 t = *reinterpret_cast<const float4*>(tile + r * 36 + (lane & 7) * 4);
+            if (row0 + r < M) *reinterpret_cast<float4*>(Cb + (long long)(row0 + r) * epi.ldc + col0 + (lane & 7) * 4) = t;
+          }
+          __syncwarp();
+          continue;
         }
         if (row < M && col0 < N) {
           // general epilogue: raw addend E, alpha, diagonal, beta*(D [+ D_lo]), ReLU / rounding, plain / (hi, lo) / transposed
@@ -355,7 +368,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   const int triple = tmAl ? 1 : 0;
   const int max_stages = triple ? Cfg::STAGES / 2 : Cfg::STAGES;
   const int nstages = kblocks_per_cta < max_stages ? (int)kblocks_per_cta : max_stages;
-  const int smem = nstages * Cfg::STAGE_BYTES * (triple ? 2 : 1) + 1024 + 256;
+  const int smem = nstages * Cfg::STAGE_BYTES * (triple ? 2 : 1) + 1024 + 256 + Cfg::EPI_TILE;
   const int grid = total < sms ? (int)total : sms;
   umma_gemm_kernel<BN><<<grid, 192, smem, stream>>>(tmA, tmB, triple ? *tmAl : tmA, triple ? *tmBl : tmB, triple, epi, M, N, K,
                                                     a_mn, b_mn, shareA, shareB,

@@ -62,7 +62,7 @@ __global__ void bn_stats_partial_kernel(const float* __restrict__ x, float* __re
   for (int c4 = cl; c4 < C4; c4 += clanes) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
     if (pl < plan) {
-#pragma unroll 4
+#pragma unroll 8
       for (long long p = p0 + pl; p < p1; p += plan) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * C) + c4);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
@@ -84,13 +84,17 @@ __global__ void bn_stats_partial_kernel(const float* __restrict__ x, float* __re
 __global__ void bn_stats_finalize_kernel(const float* __restrict__ part, int nblk, long long P, int C, float eps,
                                          float momentum, float* __restrict__ mean, float* __restrict__ invstd,
                                          float* __restrict__ rmean, float* __restrict__ rvar) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per channel
-  const int lane = threadIdx.x & 31;
-  if (c >= C) return;
+  // block = 32 channels x 8 partial-row lanes: lanes run along channels (coalesced 128 B reads of the partial rows)
+  __shared__ double red[2][8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   double s = 0.0, q = 0.0;
-  for (int b = lane; b < nblk; b += 32) { s += part[((size_t)b * 2) * C + c]; q += part[((size_t)b * 2 + 1) * C + c]; }
-  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-  if (lane != 0) return;
+  if (c < C)
+    for (int b = w; b < nblk; b += 8) { s += part[((size_t)b * 2) * C + c]; q += part[((size_t)b * 2 + 1) * C + c]; }
+  red[0][w][lane] = s; red[1][w][lane] = q;
+  __syncthreads();
+  if (w != 0 || c >= C) return;
+  for (int k = 1; k < 8; ++k) { s += red[0][k][lane]; q += red[1][k][lane]; }
   const double m = s / (double)P;
   double var = q / (double)P - m * m;
   if (var < 0.0) var = 0.0;
@@ -140,7 +144,7 @@ __global__ void bn_bwd_partial_kernel(const float* __restrict__ x, const float* 
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
     if (pl < plan) {
       const float4 m = reinterpret_cast<const float4*>(mean)[c4], is = reinterpret_cast<const float4*>(invstd)[c4];
-#pragma unroll 2
+#pragma unroll 4
       for (long long p = p0 + pl; p < p1; p += plan) {
         float4 g = __ldg(reinterpret_cast<const float4*>(dy + p * C) + c4);
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * C) + c4);
@@ -166,13 +170,16 @@ __global__ void bn_bwd_partial_kernel(const float* __restrict__ x, const float* 
 }
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per channel
-  const int lane = threadIdx.x & 31;
-  if (c >= C) return;
+  __shared__ double red[2][8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   double s = 0.0, q = 0.0;
-  for (int b = lane; b < nblk; b += 32) { s += part[((size_t)b * 2) * C + c]; q += part[((size_t)b * 2 + 1) * C + c]; }
-  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-  if (lane != 0) return;
+  if (c < C)
+    for (int b = w; b < nblk; b += 8) { s += part[((size_t)b * 2) * C + c]; q += part[((size_t)b * 2 + 1) * C + c]; }
+  red[0][w][lane] = s; red[1][w][lane] = q;
+  __syncthreads();
+  if (w != 0 || c >= C) return;
+  for (int k = 1; k < 8; ++k) { s += red[0][k][lane]; q += red[1][k][lane]; }
   dbeta[c] = (float)s;
   dgamma[c] = (float)q;
 }
@@ -336,7 +343,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restri
 
 static int bn_blocks(long long P) {
   long long b = (P + 255) / 256;
-  if (b > 296) b = 296;
+  if (b > 592) b = 592;      // 4 blocks per SM: the partial-sum kernels need ~8 MB of loads in flight to reach HBM bandwidth
   if (b < 1) b = 1;
   return (int)b;
 }
@@ -380,7 +387,7 @@ int hk_bn_fwd(const float* x, const float* gamma, const float* beta, const float
   const int C4 = C / 4, clanes = C4 < 256 ? C4 : 256, plan = 256 / clanes;
   bn_stats_partial_kernel<<<nb, 256, (size_t)2 * plan * C * sizeof(float), st>>>(x, part, P, C);
   HK_LAUNCH_CHECK("bn_stats_partial_kernel");
-  bn_stats_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, st>>>(part, nb, P, C, eps, momentum, save_mean, save_invstd,
+  bn_stats_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(part, nb, P, C, eps, momentum, save_mean, save_invstd,
                                                          running_mean, running_var);
   HK_LAUNCH_CHECK("bn_stats_finalize_kernel");
   bn_apply_kernel<<<rgrid((size_t)P * C4, 256), 256, 0, st>>>(x, save_mean, save_invstd, gamma, beta, residual, y,
@@ -412,7 +419,7 @@ int hk_bn_bwd(const float* x, const float* y, const float* dy, const float* gamm
   const int C4 = C / 4, clanes = C4 < 256 ? C4 : 256, plan = 256 / clanes;
   bn_bwd_partial_kernel<<<nb, 256, (size_t)2 * plan * C * sizeof(float), st>>>(x, y, dy, save_mean, save_invstd, part, P, C, relu);
   HK_LAUNCH_CHECK("bn_bwd_partial_kernel");
-  bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, st>>>(part, nb, C, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(part, nb, C, dgamma, dbeta);
   HK_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   bn_bwd_apply_kernel<<<rgrid((size_t)P * C4, 256), 256, 0, st>>>(x, y, dy, save_mean, save_invstd, gamma, dgamma, dbeta, dx,
                                                                 dres, (size_t)P * C4, C4, 1.f / (float)P, relu, precise() ? 0 : 1);
