@@ -57,7 +57,59 @@ struct ConvArgs {
   int stride;          // 1 or 2 (N,H,W above are OUTPUT dims; the input map is H*stride x W*stride)
   const float* addend; // [N,H,W,Cout] or null: raw partial sum added to the accumulator first (3xTF32 passes; may alias Y)
   int no_round;        // 1: store fp32 as is (precise mode); 0: round to tf32 (the output feeds another MMA)
+  // fused MaxPool2d(2,2) epilogue (vgg.py:59): when P != null the full-resolution map Y is NOT written; the epilogue
+  // reduces each 2x2 window across lanes (the pixel tile is a power-of-two patch, so the window partners are lane^1,
+  // lane^TW, lane^(TW+1)) and writes the pooled value plus, if code != null, the byte maxpool2x2_bwd_idx reads
+  // (bits 0-1 = first maximum in scan order, bit 2 = max > 0).
+  float* P;            // [N,H/2,W/2,Cout] (or [N,Cout,H/2,W/2] when pool_nchw)
+  unsigned char* code; // [N,H/2,W/2,Cout] or null
+  int pool_nchw;
 };
+
+// 2x2 max-pool of one 32-channel chunk held as v[32] by the thread of pixel (w, h): window partners are lanes ^1, ^TW and
+// ^(TW|1).  Written by the top-left lane of each window.  Bit-identical to maxpool2x2_fwd_idx_kernel on the stored map.
+__device__ __forceinline__ void epi_pool_store(const ConvArgs& a, const float* v, int TW, int w, int h, int n, int co,
+                                               bool valid) {
+  const bool writer = valid && !(w & 1) && !(h & 1);
+  const int Ho = a.H >> 1, Wo = a.W >> 1;
+  const size_t pp = ((size_t)n * Ho + (h >> 1)) * Wo + (w >> 1);
+  float m[32];
+  unsigned char cd[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float v0 = v[j];
+    const float v1 = __shfl_xor_sync(0xffffffffu, v0, 1);
+    const float v2 = __shfl_xor_sync(0xffffffffu, v0, TW);
+    const float v3 = __shfl_xor_sync(0xffffffffu, v0, TW | 1);
+    float mm = v0;
+    unsigned char k = 0;
+    if (v1 > mm) { mm = v1; k = 1; }
+    if (v2 > mm) { mm = v2; k = 2; }
+    if (v3 > mm) { mm = v3; k = 3; }
+    m[j] = mm;
+    cd[j] = k | (mm > 0.f ? 4 : 0);
+  }
+  if (!writer) return;
+  if (a.code) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      pk[j] = (uint32_t)cd[4 * j] | ((uint32_t)cd[4 * j + 1] << 8) | ((uint32_t)cd[4 * j + 2] << 16) | ((uint32_t)cd[4 * j + 3] << 24);
+    uint4* cp = reinterpret_cast<uint4*>(a.code + pp * a.Cout + co);
+    cp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    cp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+  if (!a.pool_nchw) {
+    float4* dst = reinterpret_cast<float4*>(a.P + pp * a.Cout + co);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
+  } else {
+    const size_t hw = (size_t)Ho * Wo;
+    float* dst = a.P + ((size_t)n * a.Cout + co) * hw + (size_t)(h >> 1) * Wo + (w >> 1);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dst[(size_t)j * hw] = m[j];
+  }
+}
 
 template <int BN>
 struct ConvCfg {
@@ -181,6 +233,10 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             v[4 * j + 3] = mm.w > 0.f ? v[4 * j + 3] : 0.f;
           }
         }
+        if (a.P) {       // (never combined with the precise-mode passes: rounded like the stored map would be)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tf32_round(v[j]);
+        } else {
         float4* dst = reinterpret_cast<float4*>(a.Y + pix * a.Cout + co);
         if (a.no_round) {
 #pragma unroll
@@ -191,7 +247,10 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             dst[j] = make_float4(tf32_round(v[4 * j]), tf32_round(v[4 * j + 1]), tf32_round(v[4 * j + 2]),
                                  tf32_round(v[4 * j + 3]));
         }
+        }
       }
+      // the window reduction is a warp-wide shuffle: every lane takes part, whether or not its own pixel is valid
+      if (a.P && co < a.Cout) epi_pool_store(a, v, a.TW, w, h, n, co, valid);
     }
   }
   tc_fence_before();
@@ -400,11 +459,17 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             v[4 * j + 3] = mm.w > 0.f ? v[4 * j + 3] : 0.f;
           }
         }
-        float4* dst = reinterpret_cast<float4*>(a.Y + pix * a.Cout + co);
+        if (a.P) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(tf32_round(v[4 * j]), tf32_round(v[4 * j + 1]), tf32_round(v[4 * j + 2]),
-                               tf32_round(v[4 * j + 3]));
+          for (int j = 0; j < 32; ++j) v[j] = tf32_round(v[j]);
+          epi_pool_store(a, v, 16, w, h, n, co, true);
+        } else {
+          float4* dst = reinterpret_cast<float4*>(a.Y + pix * a.Cout + co);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(tf32_round(v[4 * j]), tf32_round(v[4 * j + 1]), tf32_round(v[4 * j + 2]),
+                                 tf32_round(v[4 * j + 3]));
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -460,7 +525,8 @@ static int launch_conv_v2(const float* x, const float* wp, ConvArgs a, int N, in
 
 static int conv3x3_igemm_1x(const float* x, const float* wp, const float* bias, const float* mask, const float* addend,
                             float* y, int N, int H, int W, int Cin, int Cout, int relu, cudaStream_t stream, int stride,
-                            bool generic_only, int no_round);
+                            bool generic_only, int no_round, float* pooled = nullptr, unsigned char* code = nullptr,
+                            int pool_nchw = 0);
 
 // x NHWC [N,H,W,Cin], wp packed [9][Cout][Cin] -> y NHWC [N,H,W,Cout]
 int conv3x3_igemm(const float* x, const float* wp, const float* bias, const float* mask, float* y, int N, int H, int W,
@@ -482,19 +548,23 @@ int conv3x3_igemm(const float* x, const float* wp, const float* bias, const floa
 
 static int conv3x3_igemm_1x(const float* x, const float* wp, const float* bias, const float* mask, const float* addend,
                             float* y, int N, int H, int W, int Cin, int Cout, int relu, cudaStream_t stream, int stride,
-                            bool generic_only, int no_round) {
+                            bool generic_only, int no_round, float* pooled, unsigned char* code, int pool_nchw) {
   // H, W are the INPUT dims; output is H/stride x W/stride (padding 1)
   const int Hin = H, Win = W;
   if (stride == 2) {
     HK_REQUIRE(H % 2 == 0 && W % 2 == 0, HK_ERR_UNSUPPORTED, "conv3x3 stride 2: even H/W required");
     H /= 2; W /= 2;
   }
-  HK_REQUIRE(x && wp && y, HK_ERR_ARG, "conv3x3: null pointer");
+  HK_REQUIRE(x && wp && (y || pooled), HK_ERR_ARG, "conv3x3: null pointer");
   HK_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0, HK_ERR_UNSUPPORTED, "conv3x3: Cin=%d Cout=%d must be multiples of 32",
              Cin, Cout);
-  HK_REQUIRE(aligned16(x) && aligned16(wp) && aligned16(y) && (!mask || aligned16(mask)), HK_ERR_ALIGN,
+  HK_REQUIRE(aligned16(x) && aligned16(wp) && (!y || aligned16(y)) && (!mask || aligned16(mask)), HK_ERR_ALIGN,
              "conv3x3: pointer not 16-byte aligned");
+  if (pooled)
+    HK_REQUIRE(stride == 1 && H % 2 == 0 && W % 2 == 0 && aligned16(pooled) && (!code || aligned16(code)), HK_ERR_UNSUPPORTED,
+               "conv3x3 + pool: even H/W, stride 1 and 16-byte aligned outputs required");
   ConvArgs a = {};
+  a.P = pooled; a.code = code; a.pool_nchw = pool_nchw;
   a.Y = y; a.bias = bias; a.mask = mask; a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.relu = relu;
   a.stride = stride;
   a.addend = addend; a.no_round = no_round;
@@ -508,6 +578,7 @@ static int conv3x3_igemm_1x(const float* x, const float* wp, const float* bias, 
     }
   }
   pick_tile(W, H, N, 128, &a.TW, &a.TH, &a.TN);
+  HK_REQUIRE(!pooled || (a.TW >= 2 && a.TH >= 2), HK_ERR_UNSUPPORTED, "conv3x3 + pool: pixel tile %dx%d", a.TW, a.TH);
   a.tiles_w = (W + a.TW - 1) / a.TW; a.tiles_h = (H + a.TH - 1) / a.TH; a.tiles_n = (N + a.TN - 1) / a.TN;
   HK_REQUIRE((long long)a.tiles_w * a.tiles_h * a.tiles_n < (1ll << 31), HK_ERR_UNSUPPORTED, "conv3x3: grid too large");
   CUtensorMap tmX, tmW;
@@ -1184,6 +1255,17 @@ int hk_conv3x3_pack_weights(const float* w, float* w_fwd, float* w_dgrad, int Co
 int hk_conv3x3_fwd(const float* x, const float* w_packed, const float* bias, float* y, int N, int H, int W, int Cin,
                    int Cout, int relu, void* stream) {
   return conv3x3_igemm(x, w_packed, bias, nullptr, y, N, H, W, Cin, Cout, relu, (cudaStream_t)stream);
+}
+
+/* relu(conv3x3(x) + bias) followed by MaxPool2d(2,2) in ONE kernel: the full-resolution map is never written.  pooled:
+ * [N,H/2,W/2,Cout] (NHWC) or [N,Cout,H/2,W/2] (out_nchw); code (optional): the byte per pooled element hk_maxpool2x2_bwd_idx
+ * consumes.  Bit-identical to hk_conv3x3_fwd + hk_maxpool2x2_fwd_idx.  Single-pass TF32 only (HK_ERR_UNSUPPORTED in precise mode). */
+int hk_conv3x3_fwd_pool(const float* x, const float* w_packed, const float* bias, float* pooled, unsigned char* code, int N,
+                        int H, int W, int Cin, int Cout, int out_nchw, void* stream) {
+  HK_REQUIRE(!precise(), HK_ERR_UNSUPPORTED, "hk_conv3x3_fwd_pool: not available in 3xTF32 mode (use conv + pool)");
+  HK_REQUIRE(pooled, HK_ERR_ARG, "hk_conv3x3_fwd_pool: null output");
+  return conv3x3_igemm_1x(x, w_packed, bias, nullptr, nullptr, nullptr, N, H, W, Cin, Cout, 1, (cudaStream_t)stream, 1, false,
+                          0, pooled, code, out_nchw);
 }
 
 int hk_conv3x3_s2_fwd(const float* x, const float* w_packed, const float* bias, float* y, int N, int H, int W, int Cin,

@@ -84,19 +84,22 @@ __global__ void bn_stats_partial_kernel(const float* __restrict__ x, float* __re
 __global__ void bn_stats_finalize_kernel(const float* __restrict__ part, int nblk, long long P, int C, float eps,
                                          float momentum, float* __restrict__ mean, float* __restrict__ invstd,
                                          float* __restrict__ rmean, float* __restrict__ rvar) {
-  // block = 32 channels x 8 partial-row lanes: lanes run along channels (coalesced 128 B reads of the partial rows)
-  __shared__ double red[2][8][32];
+  // block = 32 channels x 32 partial-row lanes: lanes run along channels (coalesced 128 B reads of the partial rows)
+  __shared__ float red[2][32][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
-  double s = 0.0, q = 0.0;
-  if (c < C)
-    for (int b = w; b < nblk; b += 8) { s += part[((size_t)b * 2) * C + c]; q += part[((size_t)b * 2 + 1) * C + c]; }
+  float s = 0.f, q = 0.f;
+  if (c < C) {
+#pragma unroll 4
+    for (int b = w; b < nblk; b += 32) { s += part[((size_t)b * 2) * C + c]; q += part[((size_t)b * 2 + 1) * C + c]; }
+  }
   red[0][w][lane] = s; red[1][w][lane] = q;
   __syncthreads();
   if (w != 0 || c >= C) return;
-  for (int k = 1; k < 8; ++k) { s += red[0][k][lane]; q += red[1][k][lane]; }
-  const double m = s / (double)P;
-  double var = q / (double)P - m * m;
+  double sd = 0.0, qd = 0.0;
+  for (int k = 0; k < 32; ++k) { sd += (double)red[0][k][lane]; qd += (double)red[1][k][lane]; }
+  const double m = sd / (double)P;
+  double var = qd / (double)P - m * m;
   if (var < 0.0) var = 0.0;
   mean[c] = (float)m;
   invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -170,18 +173,22 @@ __global__ void bn_bwd_partial_kernel(const float* __restrict__ x, const float* 
 }
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta) {
-  __shared__ double red[2][8][32];
+  // block = 32 channels x 32 partial-row lanes: lanes run along channels (coalesced 128 B reads of the partial rows)
+  __shared__ float red[2][32][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
-  double s = 0.0, q = 0.0;
-  if (c < C)
-    for (int b = w; b < nblk; b += 8) { s += part[((size_t)b * 2) * C + c]; q += part[((size_t)b * 2 + 1) * C + c]; }
+  float s = 0.f, q = 0.f;
+  if (c < C) {
+#pragma unroll 4
+    for (int b = w; b < nblk; b += 32) { s += part[((size_t)b * 2) * C + c]; q += part[((size_t)b * 2 + 1) * C + c]; }
+  }
   red[0][w][lane] = s; red[1][w][lane] = q;
   __syncthreads();
   if (w != 0 || c >= C) return;
-  for (int k = 1; k < 8; ++k) { s += red[0][k][lane]; q += red[1][k][lane]; }
-  dbeta[c] = (float)s;
-  dgamma[c] = (float)q;
+  double sd = 0.0, qd = 0.0;
+  for (int k = 0; k < 32; ++k) { sd += (double)red[0][k][lane]; qd += (double)red[1][k][lane]; }
+  dbeta[c] = (float)sd;
+  dgamma[c] = (float)qd;
 }
 // dx = gamma*invstd*(dy' - dbeta/P - xhat*dgamma/P)  (tf32-rounded: operand of dgrad/wgrad);  dres = dy' (optional)
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
@@ -387,7 +394,7 @@ int hk_bn_fwd(const float* x, const float* gamma, const float* beta, const float
   const int C4 = C / 4, clanes = C4 < 256 ? C4 : 256, plan = 256 / clanes;
   bn_stats_partial_kernel<<<nb, 256, (size_t)2 * plan * C * sizeof(float), st>>>(x, part, P, C);
   HK_LAUNCH_CHECK("bn_stats_partial_kernel");
-  bn_stats_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(part, nb, P, C, eps, momentum, save_mean, save_invstd,
+  bn_stats_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(part, nb, P, C, eps, momentum, save_mean, save_invstd,
                                                          running_mean, running_var);
   HK_LAUNCH_CHECK("bn_stats_finalize_kernel");
   bn_apply_kernel<<<rgrid((size_t)P * C4, 256), 256, 0, st>>>(x, save_mean, save_invstd, gamma, beta, residual, y,
@@ -419,7 +426,7 @@ int hk_bn_bwd(const float* x, const float* y, const float* dy, const float* gamm
   const int C4 = C / 4, clanes = C4 < 256 ? C4 : 256, plan = 256 / clanes;
   bn_bwd_partial_kernel<<<nb, 256, (size_t)2 * plan * C * sizeof(float), st>>>(x, y, dy, save_mean, save_invstd, part, P, C, relu);
   HK_LAUNCH_CHECK("bn_bwd_partial_kernel");
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(part, nb, C, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(part, nb, C, dgamma, dbeta);
   HK_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   bn_bwd_apply_kernel<<<rgrid((size_t)P * C4, 256), 256, 0, st>>>(x, y, dy, save_mean, save_invstd, gamma, dgamma, dbeta, dx,
                                                                 dres, (size_t)P * C4, C4, 1.f / (float)P, relu, precise() ? 0 : 1);

@@ -3,6 +3,8 @@
 Every op here calls ``libhawkeye_b200.so`` through ``_lib.call``; there is no PyTorch-eager fallback.
 PyTorch owns all device buffers (caching allocator) incl. workspaces and saved-for-backward tensors.
 """
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -19,6 +21,8 @@ CAPTURE = None
 # Backbone weight/bias gradients are accumulated by the wgrad kernels directly into an existing ``param.grad`` (see
 # VGGFeaturesFn.backward).  Set to False to make every backward return fresh gradient tensors to autograd instead.
 ACCUMULATE_INTO_GRAD = True
+# conv3x3 + ReLU + MaxPool2d(2,2) as one kernel (hk_conv3x3_fwd_pool) wherever VGG has a pool after a conv
+FUSE_CONV_POOL = os.environ.get('HK_FUSE_CONV_POOL', '1') != '0'
 
 
 def _grad_ready(p):
@@ -189,11 +193,16 @@ class VGGFeaturesFn(Function):
         save = bool(train_backbone)   # decided by the caller: grad mode is always off inside Function.forward
         records = []   # per layer: dict for backward
         cur, C, li = None, 3, 0
+        # conv + ReLU + max-pool in one kernel (the pre-pool map is never written) whenever a pool follows a conv; the
+        # unfused pair stays for the 3xTF32 mode (its passes chain through the full map) and for activation capture
+        fuse_pool = FUSE_CONV_POOL and not _lib.get_precise() and CAPTURE is None
+        skip_pool = False
         for idx, ent in enumerate(plan):
             if ent[0] == 'conv':
                 cout = ent[1]
                 w, b = _f32c(params[2 * li]), params[2 * li + 1]
-                y = torch.empty(N, H, W, cout, device=dev, dtype=torch.float32)
+                fused = fuse_pool and li > 0 and idx + 1 < len(plan) and plan[idx + 1][0] == 'pool' and H % 2 == 0 and W % 2 == 0
+                y = None if fused else torch.empty(N, H, W, cout, device=dev, dtype=torch.float32)
                 if li == 0:
                     ws0 = _ws(_lib.query('hk_conv3x3_first_fwd_workspace_bytes', N, H, W, cout), dev)
                     _lib.call('hk_conv3x3_first_fwd', x, w, b, y, N, H, W, cout, ws0, ws0.numel(), s)
@@ -202,15 +211,30 @@ class VGGFeaturesFn(Function):
                     wf = torch.empty(9 * cout * C, device=dev, dtype=torch.float32)
                     wd = torch.empty(9 * cout * C, device=dev, dtype=torch.float32) if save else None
                     _lib.call('hk_conv3x3_pack_weights', w, wf, wd, cout, C, s)
-                    _lib.call('hk_conv3x3_fwd', cur, wf, b, y, N, H, W, C, cout, 1, s)
                     rec = dict(kind='conv', inp=cur, out=y, wd=wd, H=H, W=W, cin=C, cout=cout,
                                inp_is_relu=(records[-1]['kind'] != 'pool'))
+                    if fused:
+                        last = idx + 1 == len(plan) - 1
+                        Ho, Wo = H // 2, W // 2
+                        out = torch.empty((N, cout, Ho, Wo) if last else (N, Ho, Wo, cout), device=dev, dtype=torch.float32)
+                        code = torch.empty(N, Ho, Wo, cout, device=dev, dtype=torch.uint8) if save else None
+                        _lib.call('hk_conv3x3_fwd_pool', cur, wf, b, out, code, N, H, W, C, cout, 1 if last else 0, s)
+                        records.append(rec)
+                        records.append(dict(kind='pool', code=code, H=H, W=W, C=cout, last=last))
+                        cur, C, H, W = out, cout, Ho, Wo
+                        li += 1
+                        skip_pool = True
+                        continue
+                    _lib.call('hk_conv3x3_fwd', cur, wf, b, y, N, H, W, C, cout, 1, s)
                 records.append(rec)
                 if CAPTURE is not None:
                     CAPTURE.append(('relu', y))
                 cur, C = y, cout
                 li += 1
             else:
+                if skip_pool:       # already done by the conv before it
+                    skip_pool = False
+                    continue
                 last = idx == len(plan) - 1
                 Ho, Wo = H // 2, W // 2
                 out = torch.empty((N, C, Ho, Wo) if last else (N, Ho, Wo, C), device=dev, dtype=torch.float32)

@@ -104,6 +104,14 @@ int hk_conv3x3_pack_weights(const float* w, float* w_fwd, float* w_dgrad, int Co
 /* y = relu?(conv3x3(x, w) + bias): implicit GEMM on tcgen05, TMA zero-fill = padding.  Cin%32==0, Cout%32==0. */
 int hk_conv3x3_fwd(const float* x_nhwc, const float* w_fwd_packed, const float* bias, float* y_nhwc, int N, int H,
                    int W, int Cin, int Cout, int relu, void* stream);
+/* relu(conv3x3(x, w) + bias) followed by MaxPool2d(2,2) (vgg.py:59-68: every pool of VGG-16 follows a conv + ReLU) in ONE
+ * kernel: the epilogue reduces the 2x2 windows across lanes and the full-resolution map is never written.
+ * pooled: [N,H/2,W/2,Cout] NHWC, or [N,Cout,H/2,W/2] when out_nchw (the last pool feeds the pooling heads in NCHW);
+ * code (optional, training): one byte per pooled element for hk_maxpool2x2_bwd_idx (bits 0-1 first arg-max in scan order,
+ * bit 2 = max > 0).  Bit-identical to hk_conv3x3_fwd + hk_maxpool2x2_fwd_idx.  H, W even; single-pass TF32 mode only
+ * (HK_ERR_UNSUPPORTED under hk_set_precise(1): the 3xTF32 passes chain through the full-resolution map). */
+int hk_conv3x3_fwd_pool(const float* x_nhwc, const float* w_fwd_packed, const float* bias, float* pooled,
+                        unsigned char* code, int N, int H, int W, int Cin, int Cout, int out_nchw, void* stream);
 /* same with stride 2 (ResNet v1.5 down-sampling 3x3, resnet.py:116): H, W are the input dims, output is H/2 x W/2 */
 int hk_conv3x3_s2_fwd(const float* x_nhwc, const float* w_fwd_packed, const float* bias, float* y_nhwc, int N, int H,
                       int W, int Cin, int Cout, int relu, void* stream);

@@ -109,3 +109,40 @@ def test_first_layer_and_pool():
     assert rel_l2(_nchw(dx).cpu(), ref) < 1e-6
     _lib.call('hk_maxpool2x2_bwd', ag, g.float().cuda(), dx, N, H, W, 64, 1, s)
     assert rel_l2(_nchw(dx).cpu(), ref) < 1e-6
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout', [(2, 16, 32, 64, 64),     # v2 kernel, resident weights (VGG conv1_2)
+                                            (1, 16, 16, 64, 128),    # v2<128>
+                                            (2, 8, 16, 32, 64),      # v2<64>
+                                            (2, 28, 28, 128, 256),   # generic kernel, 4x4 pixel tiles
+                                            (3, 14, 14, 64, 512),    # generic kernel, 2x2 tiles, ragged batch tile
+                                            (2, 56, 56, 32, 96),     # generic kernel, 8-wide tiles, Cout % 128 != 0
+                                            (1, 4, 4, 32, 32)])
+@pytest.mark.parametrize('nchw', [0, 1])
+def test_conv_pool_fused_bit_exact(N, H, W, Cin, Cout, nchw):
+    """hk_conv3x3_fwd_pool == hk_conv3x3_fwd + hk_maxpool2x2_fwd_idx, bit for bit (pooled map AND the arg-max / ReLU byte),
+    on every conv kernel variant and both output layouts."""
+    from hawkeye_b200 import _lib
+    s = _lib.stream_ptr()
+    x = torch.relu(detgen.det((N, H, W, Cin), 21)).cuda()
+    w = detgen.det((Cout, Cin, 3, 3), 22, 0.1).cuda()
+    b = detgen.det((Cout,), 23, 0.2).cuda()
+    wf = torch.empty(9 * Cout * Cin, device='cuda')
+    wd = torch.empty(9 * Cout * Cin, device='cuda')
+    _lib.call('hk_conv3x3_pack_weights', w, wf, wd, Cout, Cin, s)
+    y = torch.empty(N, H, W, Cout, device='cuda')
+    _lib.call('hk_conv3x3_fwd', x, wf, b, y, N, H, W, Cin, Cout, 1, s)
+    shape = (N, Cout, H // 2, W // 2) if nchw else (N, H // 2, W // 2, Cout)
+    p_ref = torch.empty(shape, device='cuda')
+    c_ref = torch.empty(N, H // 2, W // 2, Cout, device='cuda', dtype=torch.uint8)
+    _lib.call('hk_maxpool2x2_fwd_idx', y, p_ref, c_ref, N, H, W, Cout, nchw, s)
+    p = torch.full(shape, -7.0, device='cuda')
+    c = torch.full((N, H // 2, W // 2, Cout), 255, device='cuda', dtype=torch.uint8)
+    _lib.call('hk_conv3x3_fwd_pool', x, wf, b, p, c, N, H, W, Cin, Cout, nchw, s)
+    torch.cuda.synchronize()
+    assert torch.equal(p, p_ref)
+    assert torch.equal(c, c_ref)
+    # without the code byte (inference / frozen backbone)
+    p2 = torch.empty(shape, device='cuda')
+    _lib.call('hk_conv3x3_fwd_pool', x, wf, b, p2, None, N, H, W, Cin, Cout, nchw, s)
+    assert torch.equal(p2, p_ref)
