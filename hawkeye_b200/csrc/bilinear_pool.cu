@@ -95,7 +95,9 @@ struct GramArgs {
   float* inv_norm;       // mode 0: written [B]; mode 1: read [B]
   const float* dY;       // mode 1
   float* S;              // mode 1: [B][C][C]
-  float* c_raw;          // mode 1: [B] (pre-zeroed)
+  double* c_raw;         // mode 1: [B] (pre-zeroed).  fp64: the 80 atomic partial sums of an image then give the same fp32
+                         // value in any order (an fp32 atomic sum made the whole backward run-to-run different at the tf32
+                         // rounding level, tests/diag/bimodal_debug.py)
   const int* h1;         // mode 2
   const int* h2;
   const float* s1;
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_pair_kernel(const __grid
       if (lane == 0) mbar_arrive(&acc_empty[set]);     // 8 warp arrivals free the accumulator set
       if (MODE == MODE_BCNN_BWD_S) {
         craw = warp_sum(craw);
-        if (lane == 0) atomicAdd(&a.c_raw[b], craw);
+        if (lane == 0) atomicAdd(&a.c_raw[b], (double)craw);
       }
     }
   }
@@ -398,7 +400,7 @@ __global__ void bilinear_finish_kernel(float* __restrict__ y, float* __restrict_
 }
 // S (holding the raw Gram) -> S[i][j] = (dY[i][j] + dY[j][i]) / (2 z_ij);  inv_norm[b] = 1/||z||, c_raw[b] = <dY, z>
 __global__ void bilinear_bwd_s_kernel(float* __restrict__ S, const float* __restrict__ dY, float* __restrict__ inv_norm,
-                                      float* __restrict__ c_raw, int C, float inv_hw, float eps) {
+                                      double* __restrict__ c_raw, int C, float inv_hw, float eps) {
   __shared__ float red[2][32];
   const size_t CC = (size_t)C * C;
   float* Sb = S + blockIdx.x * CC;
@@ -420,7 +422,7 @@ __global__ void bilinear_bwd_s_kernel(float* __restrict__ S, const float* __rest
     float a = 0.f, b = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; b += red[1][i]; }
     inv_norm[blockIdx.x] = 1.f / fmaxf(sqrtf(a), 1e-12f);
-    c_raw[blockIdx.x] = b;
+    c_raw[blockIdx.x] = (double)b;
   }
 }
 // bins[b][(h1[i]+h2[j]) mod d] += s1[i] s2[j] G[b][i][j]
@@ -483,13 +485,13 @@ static inline size_t colsum_smem(int HW) {
 }
 
 // per-batch scalars for the bilinear backward epilogue:  alpha = 1/(n HW),  beta = -(c_raw/n^2) / (n HW)
-__global__ void bilinear_bwd_scalars_kernel(const float* inv_norm, const float* c_raw, float inv_hw, float* alpha,
+__global__ void bilinear_bwd_scalars_kernel(const float* inv_norm, const double* c_raw, float inv_hw, float* alpha,
                                             float* beta, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) {
     const float in = inv_norm[b];
     alpha[b] = in * inv_hw;
-    beta[b] = -(c_raw[b] * in * in) * in * inv_hw;
+    beta[b] = -((float)c_raw[b] * in * in) * in * inv_hw;
   }
 }
 
@@ -526,7 +528,7 @@ __global__ void norm_from_s_kernel(const float* s, float* inv_norm, int C, int H
 
 namespace hk {
 static int bilinear_bwd_impl(const float* x, const float* dy, float* dx, int B, int C, int HW, float inv_hw, float* S,
-                             float* partial, float* svec, float* invn, float* craw, float* alpha, float* beta,
+                             float* partial, float* svec, float* invn, double* craw, float* alpha, float* beta,
                              cudaStream_t stream);
 }
 
@@ -610,9 +612,9 @@ int hk_bilinear_pool_fwd(const float* x, float* y, float* inv_norm_out, int B, i
 }
 
 size_t hk_bilinear_pool_bwd_workspace_bytes(int B, int C, int HW) {
-  // S [B,C,C] + partial [B,CS,HWp] + s [B,HWp] + inv_norm,c_raw,alpha,beta [4B] (+ padded copies of x and dx when H*W % 4 != 0)
+  // S [B,C,C] + partial [B,CS,HWp] + s [B,HWp] + inv_norm, c_raw (fp64), alpha, beta [5B] (+ padded copies of x and dx when H*W % 4 != 0)
   const int HWp = pad4(HW);
-  return ((size_t)B * C * C + (size_t)B * COLSUM_SPLITS * HWp + (size_t)B * HWp + 4 * (size_t)pad4(B) + 64 +
+  return ((size_t)B * C * C + (size_t)B * COLSUM_SPLITS * HWp + (size_t)B * HWp + 5 * (size_t)pad4(B) + 64 +
           (HWp != HW ? 2 * (size_t)B * C * HWp : 0)) * sizeof(float);
 }
 
@@ -630,8 +632,8 @@ int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int 
   float* partial = S + (size_t)B * C * C;
   float* svec = partial + (size_t)B * COLSUM_SPLITS * HWp;
   float* invn = svec + (size_t)B * HWp;
-  float* craw = invn + pad4(B);
-  float* alpha = craw + pad4(B);
+  double* craw = reinterpret_cast<double*>(invn + pad4(B));      // 16-byte aligned: every block before it is a multiple of 4 floats
+  float* alpha = invn + 3 * pad4(B);
   float* beta = alpha + pad4(B);
   float* dx_out = dx;
   if (HWp != HW) {      // zero-padded copy of x; dx is produced padded and copied back at the end
@@ -650,7 +652,7 @@ int hk_bilinear_pool_bwd(const float* x, const float* dy, float* dx, int B, int 
 
 namespace hk {
 static int bilinear_bwd_impl(const float* x, const float* dy, float* dx, int B, int C, int HW, float inv_hw, float* S,
-                             float* partial, float* svec, float* invn, float* craw, float* alpha, float* beta,
+                             float* partial, float* svec, float* invn, double* craw, float* alpha, float* beta,
                              cudaStream_t stream) {
   void* stream_ = stream;
   int r;
@@ -672,7 +674,8 @@ static int bilinear_bwd_impl(const float* x, const float* dy, float* dx, int B, 
   }
   CUtensorMap tm;
   if ((r = make_x_map(&tm, x, B, C, HW))) return r;
-  colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, colsum_smem(HW), stream>>>(x, partial, C, HW, COLSUM_SPLITS, craw, nullptr, 1);
+  colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, colsum_smem(HW), stream>>>(x, partial, C, HW, COLSUM_SPLITS,
+                                                                                reinterpret_cast<float*>(craw), nullptr, 2);
   HK_LAUNCH_CHECK("colsum_partial_kernel");
   // s_p = sum_c x_cp (also the rank-1 correction vector of the backward); the norm follows in closed form
   colsum_finish_kernel<<<B, 256, 0, stream>>>(partial, svec, COLSUM_SPLITS, HW);

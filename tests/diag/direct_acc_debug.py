@@ -12,7 +12,8 @@ class Cfg(dict):
 net = hb.MODEL.get('BCNN')(Cfg(name='BCNN', stage=2, num_classes=200))
 net.load_state_dict(detgen.vgg_bcnn_state(VGG16_D, 200, seed=100))
 net = net.cuda().train()
-x = detgen.det((2, 3, 64, 64), 41).cuda()
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+x = detgen.det((2, 3, S, S), 41).cuda()
 labels = detgen.det_labels(2, 200, 42).cuda()
 def backward():
     ops.CrossEntropyLS(0.1)(net(x), labels).backward()
@@ -29,5 +30,13 @@ for p in net.parameters():
 backward()
 for k, p in net.named_parameters():
     e = rel_l2(p.grad.cpu(), ref[k].cpu())
-    if e > 1e-6: print('acc vs fresh', k, e)
+    pass
+acc1 = {k: p.grad.clone() for k, p in net.named_parameters()}
+for p in net.parameters():
+    p.grad = torch.zeros_like(p)
+backward()
+worst = max(rel_l2(p.grad.cpu(), acc1[k].cpu()) for k, p in net.named_parameters())
+print('acc vs acc worst', worst)
+worst = max(rel_l2(p.grad.cpu(), ref[k].cpu()) for k, p in net.named_parameters())
+print('acc vs fresh worst', worst)
 print('done')
