@@ -311,7 +311,8 @@ struct ConvV2Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + (RESIDENT ? 0 : 3 * B_TILE);
   static constexpr int STAGES = RESIDENT ? 3 : (BN == 64 ? 4 : 3);
   static constexpr int WRES_BYTES = RESIDENT ? 18 * B_TILE : 0;      // 9 taps x 2 chunks
-  static constexpr int SMEM = STAGES * STAGE_BYTES + WRES_BYTES + 1024 + 512;
+  static constexpr int EPI_TILE = 4 * 32 * 36 * 4;                   // four epilogue warps x a 32 x 36-float transpose tile
+  static constexpr int SMEM = STAGES * STAGE_BYTES + WRES_BYTES + 1024 + 512 + EPI_TILE;
 };
 
 template <int BN, bool RESIDENT>
@@ -329,6 +330,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* wbar = acc_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  float* epi_tiles = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = a.Cin / 32;
@@ -464,11 +466,23 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           for (int j = 0; j < 32; ++j) v[j] = tf32_round(v[j]);
           epi_pool_store(a, v, 16, w, h, n, co, true);
         } else {
-          float4* dst = reinterpret_cast<float4*>(a.Y + pix * a.Cout + co);
+          // thread = pixel owning 32 consecutive channels: a direct float4 store instruction would touch 32 pixels x 16 B
+          // (half-written sectors).  Transposed through a warp-private tile, every store instruction writes the full 128 B
+          // of four pixels.
+          float* tile = epi_tiles + q * (32 * 36);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(tf32_round(v[4 * j]), tf32_round(v[4 * j + 1]), tf32_round(v[4 * j + 2]),
-                                 tf32_round(v[4 * j + 3]));
+            *reinterpret_cast<float4*>(tile + lane * 36 + 4 * j) =
+                make_float4(tf32_round(v[4 * j]), tf32_round(v[4 * j + 1]), tf32_round(v[4 * j + 2]), tf32_round(v[4 * j + 3]));
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3);                      // pixel (lane) rr of this warp: wi = rr & 15, hi = 2 q + (rr >> 4)
+            const size_t pr = ((size_t)n * a.H + (th * 8 + q * 2 + (rr >> 4))) * a.W + tw * 16 + (rr & 15);
+            *reinterpret_cast<float4*>(a.Y + pr * a.Cout + co + (lane & 7) * 4) =
+                *reinterpret_cast<const float4*>(tile + rr * 36 + (lane & 7) * 4);
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();

@@ -55,7 +55,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = (K + 31) / 32;
-  constexpr int TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
+  // triple mode keeps TWO accumulators per tile — the leading product Ah.Bh and the sum of the two correction products —
+  // and adds them in the epilogue: the tensor core's accumulator addition truncates, so feeding terms 2^-11 the size of the
+  // running sum into it loses them with a bias (the MPN 224x224 reference-gradient test moved by 10x when they shared one)
+  const int acc_cols = triple ? 2 * BN : BN;
+  const int TCOLS = 2 * acc_cols < 32 ? 32 : 2 * acc_cols;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -135,7 +139,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int set = itl & 1;
         mbar_wait(&acc_empty[set], ((itl >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + set * BN;
+        const uint32_t d = tmem_base + set * acc_cols;
+        const uint32_t d_small = d + BN;
         for (int kb = 0; kb < nk; ++kb, ++kbg) {
           const int s = kbg % nstages;
           const uint32_t ph = (kbg / nstages) & 1;
@@ -150,9 +155,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint64_t al_base = a_tmpl + (smem_u32(sAl + s * Cfg::A_BYTES) >> 4);
               const uint64_t bl_base = b_tmpl + (smem_u32(sBl + s * Cfg::B_BYTES) >> 4);
               for (int ks = 0; ks < ksteps; ++ks) {
-                umma_tf32_ss(d, a_base + ks * a_step, bl_base + ks * b_step, idesc, (kb | ks) ? 1u : 0u);
-                umma_tf32_ss(d, al_base + ks * a_step, b_base + ks * b_step, idesc, 1u);
-                umma_tf32_ss(d, a_base + ks * a_step, b_base + ks * b_step, idesc, 1u);
+                umma_tf32_ss(d_small, a_base + ks * a_step, bl_base + ks * b_step, idesc, (kb | ks) ? 1u : 0u);
+                umma_tf32_ss(d_small, al_base + ks * a_step, b_base + ks * b_step, idesc, 1u);
+                umma_tf32_ss(d, a_base + ks * a_step, b_base + ks * b_step, idesc, (kb | ks) ? 1u : 0u);
               }
             } else {
               for (int ks = 0; ks < ksteps; ++ks)
@@ -190,8 +195,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         float v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + set * BN + c * 32, v);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + set * acc_cols + c * 32, v);
         tmem_ld_wait();
+        if (triple) {
+          float sm[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + set * acc_cols + BN + c * 32, sm);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += sm[j];
+        }
         const int col0 = n0 + c * 32;
         // fast path (plain scaled store of a full, aligned 32-column chunk): a handful of instructions per element — the
         // general path below costs ~60 and dominates short-K GEMMs such as the first VGG layer (K = 32)
@@ -462,15 +474,14 @@ int gemm_tf32_pair(const float* Ah, const float* Al, int a_mn, long long lda, lo
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
   // 128-wide tiles while 256-wide ones would leave SMs idle (Newton-Schulz: n = 256, batch 32 -> 128 tiles instead of 64)
-  int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-  if (BN == 256 && (long long)((M + 127) / 128) * ((N + 255) / 256) * batch < sms) BN = 128;
+  // two accumulators per tile x double buffering = 4 BN TMEM columns: BN <= 128
+  const int BN = N <= 64 ? 64 : 128;
   if ((r = make_operand_map(&tmA, Ah, a_mn, lda, strideA, M, K, batch, 128, &shareA))) return r;
   if ((r = make_operand_map(&tmAl, Al, a_mn, lda, strideA, M, K, batch, 128, &shareA))) return r;
   if ((r = make_operand_map(&tmB, Bh, b_mn, ldb, strideB, N, K, batch, BN, &shareB))) return r;
   if ((r = make_operand_map(&tmBl, Bl, b_mn, ldb, strideB, N, K, batch, BN, &shareB))) return r;
   if (BN == 64) return launch_gemm<64>(tmA, tmB, epi, M, N, K, batch, a_mn, b_mn, shareA, shareB, stream, &tmAl, &tmBl);
-  if (BN == 128) return launch_gemm<128>(tmA, tmB, epi, M, N, K, batch, a_mn, b_mn, shareA, shareB, stream, &tmAl, &tmBl);
-  return launch_gemm<256>(tmA, tmB, epi, M, N, K, batch, a_mn, b_mn, shareA, shareB, stream, &tmAl, &tmBl);
+  return launch_gemm<128>(tmA, tmB, epi, M, N, K, batch, a_mn, b_mn, shareA, shareB, stream, &tmAl, &tmBl);
 }
 
 }  // namespace hk
