@@ -132,9 +132,12 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 // backward reductions: part[blk][0][c] = sum dy', part[blk][1][c] = sum dy' * xhat,  dy' = dy * (y > 0 if relu)
+// relu with gamma/beta given (and no residual in the forward): the ReLU mask is recomputed from x with the forward's own
+// expression, so y (a third of the bytes) is not read at all
 __global__ void bn_bwd_partial_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                       const float* __restrict__ dy, const float* __restrict__ mean,
-                                      const float* __restrict__ invstd, float* __restrict__ part, long long P, int C,
+                                      const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float* __restrict__ part, long long P, int C,
                                       int relu) {
   extern __shared__ float sm[];
   const int C4 = C / 4;
@@ -147,11 +150,16 @@ __global__ void bn_bwd_partial_kernel(const float* __restrict__ x, const float* 
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
     if (pl < plan) {
       const float4 m = reinterpret_cast<const float4*>(mean)[c4], is = reinterpret_cast<const float4*>(invstd)[c4];
+      float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), be = ga;
+      if (relu && beta) { ga = reinterpret_cast<const float4*>(gamma)[c4]; be = reinterpret_cast<const float4*>(beta)[c4]; }
 #pragma unroll 4
       for (long long p = p0 + pl; p < p1; p += plan) {
         float4 g = __ldg(reinterpret_cast<const float4*>(dy + p * C) + c4);
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * C) + c4);
-        if (relu) {
+        if (relu && beta) {
+          g.x = fmaf((v.x - m.x) * is.x, ga.x, be.x) > 0.f ? g.x : 0.f; g.y = fmaf((v.y - m.y) * is.y, ga.y, be.y) > 0.f ? g.y : 0.f;
+          g.z = fmaf((v.z - m.z) * is.z, ga.z, be.z) > 0.f ? g.z : 0.f; g.w = fmaf((v.w - m.w) * is.w, ga.w, be.w) > 0.f ? g.w : 0.f;
+        } else if (relu) {
           const float4 o = __ldg(reinterpret_cast<const float4*>(y + p * C) + c4);
           g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
         }
@@ -195,19 +203,23 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __
                                     const float* __restrict__ dy, const float* __restrict__ mean,
                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
                                     const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-                                    float* __restrict__ dx, float* __restrict__ dres, size_t total4, int C4, float invP,
-                                    int relu, int round) {
+                                    const float* __restrict__ beta, float* __restrict__ dx, float* __restrict__ dres,
+                                    size_t total4, int C4, float invP, int relu, int round) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
     float4 g = reinterpret_cast<const float4*>(dy)[i];
     const float4 v = reinterpret_cast<const float4*>(x)[i];
-    if (relu) {
+    const float4 m = reinterpret_cast<const float4*>(mean)[c4], is = reinterpret_cast<const float4*>(invstd)[c4];
+    const float4 ga = reinterpret_cast<const float4*>(gamma)[c4];
+    if (relu && beta) {
+      const float4 be = reinterpret_cast<const float4*>(beta)[c4];
+      g.x = fmaf((v.x - m.x) * is.x, ga.x, be.x) > 0.f ? g.x : 0.f; g.y = fmaf((v.y - m.y) * is.y, ga.y, be.y) > 0.f ? g.y : 0.f;
+      g.z = fmaf((v.z - m.z) * is.z, ga.z, be.z) > 0.f ? g.z : 0.f; g.w = fmaf((v.w - m.w) * is.w, ga.w, be.w) > 0.f ? g.w : 0.f;
+    } else if (relu) {
       const float4 o = reinterpret_cast<const float4*>(y)[i];
       g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
     }
     if (dres) reinterpret_cast<float4*>(dres)[i] = g;
-    const float4 m = reinterpret_cast<const float4*>(mean)[c4], is = reinterpret_cast<const float4*>(invstd)[c4];
-    const float4 ga = reinterpret_cast<const float4*>(gamma)[c4];
     const float4 dg = reinterpret_cast<const float4*>(dgamma)[c4], db = reinterpret_cast<const float4*>(dbeta)[c4];
     float4 o;
     o.x = ga.x * is.x * (g.x - db.x * invP - (v.x - m.x) * is.x * dg.x * invP);
@@ -413,23 +425,34 @@ int hk_bn_apply(const float* x, const float* mean, const float* invstd, const fl
   return 0;
 }
 
+int hk_bn_bwd_ex(const float* x, const float* y, const float* dy, const float* gamma, const float* beta_for_mask,
+                 const float* save_mean, const float* save_invstd, float* dx, float* dres, float* dgamma, float* dbeta,
+                 long long P, int C, int relu, void* workspace, size_t workspace_bytes, void* stream_);
 int hk_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
               const float* save_invstd, float* dx, float* dres, float* dgamma, float* dbeta, long long P, int C, int relu,
               void* workspace, size_t workspace_bytes, void* stream_) {
+  return hk_bn_bwd_ex(x, y, dy, gamma, nullptr, save_mean, save_invstd, dx, dres, dgamma, dbeta, P, C, relu, workspace,
+                      workspace_bytes, stream_);
+}
+int hk_bn_bwd_ex(const float* x, const float* y, const float* dy, const float* gamma, const float* beta_for_mask,
+                 const float* save_mean, const float* save_invstd, float* dx, float* dres, float* dgamma, float* dbeta,
+                 long long P, int C, int relu, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  HK_REQUIRE(x && dy && gamma && save_mean && save_invstd && dx && dgamma && dbeta && (!relu || y), HK_ERR_ARG,
+  const float* beta = relu ? beta_for_mask : nullptr;
+  HK_REQUIRE(x && dy && gamma && save_mean && save_invstd && dx && dgamma && dbeta && (!relu || y || beta), HK_ERR_ARG,
              "hk_bn_bwd: null pointer");
   HK_REQUIRE(C % 4 == 0 && P > 0, HK_ERR_UNSUPPORTED, "hk_bn_bwd: C=%d must be a multiple of 4", C);
   HK_REQUIRE(workspace && workspace_bytes >= hk_bn_workspace_bytes(P, C), HK_ERR_WORKSPACE, "hk_bn_bwd: workspace too small");
   float* part = static_cast<float*>(workspace);
   const int nb = bn_blocks(P);
   const int C4 = C / 4, clanes = C4 < 256 ? C4 : 256, plan = 256 / clanes;
-  bn_bwd_partial_kernel<<<nb, 256, (size_t)2 * plan * C * sizeof(float), st>>>(x, y, dy, save_mean, save_invstd, part, P, C, relu);
+  bn_bwd_partial_kernel<<<nb, 256, (size_t)2 * plan * C * sizeof(float), st>>>(x, y, dy, save_mean, save_invstd, gamma, beta, part, P,
+                                                                               C, relu);
   HK_LAUNCH_CHECK("bn_bwd_partial_kernel");
   bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(part, nb, C, dgamma, dbeta);
   HK_LAUNCH_CHECK("bn_bwd_finalize_kernel");
-  bn_bwd_apply_kernel<<<rgrid((size_t)P * C4, 256), 256, 0, st>>>(x, y, dy, save_mean, save_invstd, gamma, dgamma, dbeta, dx,
-                                                                dres, (size_t)P * C4, C4, 1.f / (float)P, relu, precise() ? 0 : 1);
+  bn_bwd_apply_kernel<<<rgrid((size_t)P * C4, 256), 256, 0, st>>>(x, y, dy, save_mean, save_invstd, gamma, dgamma, dbeta, beta,
+                                                                dx, dres, (size_t)P * C4, C4, 1.f / (float)P, relu, precise() ? 0 : 1);
   HK_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return 0;
 }

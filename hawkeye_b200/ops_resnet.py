@@ -87,7 +87,7 @@ class Unit:
         if _ops.CAPTURE is not None and self.relu:
             _ops.CAPTURE.append(('relu', y))
         if save:
-            rec.update(c=c, y=y if self.relu else None, mean=mean, invstd=invstd, P=P, cout=cout, w=w, gamma=gamma,
+            rec.update(c=c, y=y if self.relu else None, mean=mean, invstd=invstd, P=P, cout=cout, w=w, gamma=gamma, beta=beta,
                        shape=(N, Ho, Wo), has_res=residual is not None)
             return y, rec
         return y, None
@@ -103,8 +103,10 @@ class Unit:
         dgamma = torch.empty(cout, device=dev, dtype=torch.float32)
         dbeta = torch.empty(cout, device=dev, dtype=torch.float32)
         ws = _ws(_lib.query('hk_bn_workspace_bytes', P, cout), dev)
-        _lib.call('hk_bn_bwd', rec['c'], rec['y'], dy, rec['gamma'], rec['mean'], rec['invstd'], dc, dres, dgamma, dbeta,
-                  P, cout, int(self.relu), ws, ws.numel(), s)
+        # BN + ReLU without a residual: the mask is recomputed from x (hk_bn_bwd_ex), y is not read
+        mask_beta = rec['beta'] if (self.relu and not rec['has_res'] and rec.get('train_stats', True)) else None
+        _lib.call('hk_bn_bwd_ex', rec['c'], rec['y'], dy, rec['gamma'], mask_beta, rec['mean'], rec['invstd'], dc, dres,
+                  dgamma, dbeta, P, cout, int(self.relu), ws, ws.numel(), s)
         w, xin = rec['w'], rec['xin']
         dx = None
         if self.kind == 'stem':

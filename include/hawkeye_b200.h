@@ -164,6 +164,13 @@ int hk_bn_apply(const float* x, const float* mean, const float* invstd, const fl
 int hk_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
               const float* save_invstd, float* dx, float* dres, float* dgamma, float* dbeta, long long P, int C, int relu,
               void* workspace, size_t workspace_bytes, void* stream);
+/* hk_bn_bwd with the ReLU mask recomputed instead of read: when the forward was relu((x-mean)*invstd*gamma + beta) WITHOUT a
+ * residual, pass that beta as beta_for_mask and the backward re-evaluates the forward's own expression on x (same operation
+ * order, so the same mask) — y is not read (may be null): a third less HBM traffic in both backward passes.
+ * beta_for_mask == null: identical to hk_bn_bwd (mask = y > 0). */
+int hk_bn_bwd_ex(const float* x, const float* y, const float* dy, const float* gamma, const float* beta_for_mask,
+                 const float* save_mean, const float* save_invstd, float* dx, float* dres, float* dgamma, float* dbeta,
+                 long long P, int C, int relu, void* workspace, size_t workspace_bytes, void* stream);
 /* nn.MaxPool2d(3, 2, 1) (resnet.py:180) */
 /* argmax (optional, [N,Ho,Wo,C] bytes): window position of the first maximum, consumed by the backward */
 int hk_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* argmax, int N, int H, int W, int C, void* stream);

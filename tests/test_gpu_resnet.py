@@ -54,6 +54,12 @@ def test_batchnorm_train(N, H, W, C, relu, res):
     assert rel_l2(dg.cpu(), grads[1]) < 2e-3 and rel_l2(db.cpu(), grads[2]) < 2e-3
     if res:
         assert rel_l2(_nchw(dres).cpu(), grads[3]) < 1e-6
+    if relu and not res:
+        # hk_bn_bwd_ex: the ReLU mask re-evaluated from x (y not read, passed as null) must give the same bits
+        dx2, dg2, db2 = torch.empty_like(xg), torch.empty(C, device='cuda'), torch.empty(C, device='cuda')
+        _lib.call('hk_bn_bwd_ex', xg, None, _nhwc(dy).cuda(), gamma.cuda(), beta.cuda(), mean, invstd, dx2, None, dg2, db2, P, C,
+                  relu, ws, nb, s)
+        assert torch.equal(dx2, dx) and torch.equal(dg2, dg) and torch.equal(db2, db)
 
 
 def test_maxpool3x3_s2_and_stride_helpers():
