@@ -14,7 +14,7 @@ python profiles/summarize_launches.py gpurun_out/launches_$R.csv > gpurun_out/la
 for what in "$@"; do
   if [ "$what" = "gram" ]; then
     for B in 32 256; do
-      ncu --set full --clock-control none --import-source on -k regex:"bcnn_gram_fwd|bcnn_cluster_fwd" -c 2 -o gpurun_out/prof_gram_${R}_B$B -f \
+      ncu --set full --clock-control none --import-source on -k regex:"bcnn_gram_fwd|bcnn_cluster_fwd|bcnn_super_fwd" -c 2 -o gpurun_out/prof_gram_${R}_B$B -f \
           python tests/prof_bilinear.py $B > gpurun_out/prof_gram_${R}_B$B.log 2>&1
       ncu -i gpurun_out/prof_gram_${R}_B$B.ncu-rep --page raw --csv > gpurun_out/prof_gram_${R}_B$B.raw.csv 2>/dev/null
     done
