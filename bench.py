@@ -39,7 +39,7 @@ RESNET50_MPN_FWD_GFLOP_PER_IMG = 32.9
 MPNCOV_GFLOP_PER_IMG = 1.77         # covariance + 5-iteration Newton-Schulz, forward + backward
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/ (see
 # profiles/README.md for the file each number comes from); None = not captured for this build
-K1_DRAM_TRAFFIC = {32: 12.89e6, 256: 102.82e6 + 209.68e6}     # profiles/gram_r2f_metrics.txt (tests/prof_bilinear.py 32 / 256)
+K1_DRAM_TRAFFIC = {32: 12.89e6 + 0.01e6, 256: 102.83e6 + 210.72e6}   # profiles/gram_r3_metrics.txt (tests/prof_bilinear.py 32 / 256)
 WORKLOADS = {
     'bcnn_s2': dict(cfg='BCNN_S2.yaml', trainer='BCNN', model='BCNN VGG-16 stage 2', fwd_gflop=VGG16_FWD_GFLOP_PER_IMG, bwd_mult=3.0),
     'bcnn_s1': dict(cfg='BCNN_S1.yaml', trainer='BCNN', model='BCNN VGG-16 stage 1 (classifier only)', fwd_gflop=VGG16_FWD_GFLOP_PER_IMG, bwd_mult=1.0),
@@ -513,10 +513,12 @@ def main():
             return {'achieved': a, 'frac': a / hbm_peak, 'us_per_launch': t * 1e6}
         r32 = bw(32, t32, K1_FWD_BYTES_PER_IMG)
         line['roofline'] = {
-            'kernel': 'hk_bilinear_pool_fwd = bcnn_gram_fwd_kernel<512> (one launch: Gram + sqrt + L2 normalise; persistent '
-                      '128x128 tiles, bounded-wait norm exchange), B=32 (the per-GPU batch of this workload), C=512, HW=196',
+            'kernel': 'hk_bilinear_pool_fwd, one launch: Gram + sqrt + L2 normalise.  B=32 (the per-GPU batch of this workload, '
+                      'C=512, HW=196) = bcnn_super_fwd_kernel<true>: one wave of 4-CTA clusters, four operand-sharing items per '
+                      'image, DSMEM norm exchange; b256 / b1024 = bcnn_gram_fwd_kernel<512>: persistent 128x128 tiles, '
+                      'bounded-wait norm exchange',
             'bound': 'hbm', 'achieved': r32['achieved'], 'peak': hbm_peak, 'unit': 'GB/s', 'frac': r32['frac'],
-            'traffic': K1_DRAM_TRAFFIC[32], 'peak_source': which, 'us_per_launch': r32['us_per_launch'],
+            'traffic': K1_DRAM_TRAFFIC[32], 'traffic_note': 'ncu dram read+write per launch: the 33.5 MB output of a B=32 launch stays in the 126 MB L2 under ncu (serialised launches); in the timed back-to-back series it is written back while later launches run', 'peak_source': which, 'us_per_launch': r32['us_per_launch'],
             'algorithmic_bytes_per_launch': 32 * K1_FWD_BYTES_PER_IMG,
             'b256': dict(bw(256, t256, K1_FWD_BYTES_PER_IMG), traffic=K1_DRAM_TRAFFIC[256]),
             'b1024': bw(1024, t1024, K1_FWD_BYTES_PER_IMG)}

@@ -1,5 +1,5 @@
 """Trainer subclasses of the hot-path methods with the reference's Examples/ surface:
-``python -m hawkeye_b200.examples {BCNN,CBCNN,MPN,PeerLearning} --config <yaml>`` replaces
+``python -m hawkeye_b200.examples {BCNN,CBCNN,MPN,PeerLearning,OSMENet} --config <yaml>`` replaces
 ``python Examples/<Method>.py --config <yaml>`` (same yaml files; one process per GPU under torchrun instead of nn.DataParallel).
 
 Only what the reference's Examples override is overridden here: which parameters train, with which learning rates, and
@@ -54,7 +54,52 @@ class MPNTrainer(Trainer):
         return _warmup_cosine(self.optimizer, config, self.total_epoch)
 
 
-TRAINERS = {'BCNN': BCNNTrainer, 'CBCNN': CBCNNTrainer, 'MPN': MPNTrainer, 'PeerLearning': PeerLearningTrainer}
+class OSMENetTrainer(Trainer):
+    """Examples/OSMENet.py:10-80: the model returns (logits, per-attention features); criterion = MAMCLoss (cross-entropy +
+    lambda_a x N-pairs over the attention features); SGD with the backbone at 0.1 x lr; linear warm-up into cosine annealing.
+    The reference draws class-balanced batches (dataset/sampler.py BalancedBatchSampler: n_classes x n_samples) so that every
+    anchor has same-class partners; with a user-supplied dataloader that is the caller's business, as in the reference."""
+
+    def get_criterion(self, config):
+        from .losses import MAMCLoss
+        return MAMCLoss(config)
+
+    def param_groups(self):
+        m = self.get_model_module()
+        backbone = {id(p) for p in m.backbone.parameters()}
+        return [(list(m.backbone.parameters()), 0.1), ([p for p in m.parameters() if id(p) not in backbone], 1.0)]
+
+    def get_scheduler(self, config):
+        return _warmup_cosine(self.optimizer, config, self.total_epoch)
+
+    def batch_training(self, data):
+        import torch
+        images, labels, slot = self.stage_inputs(data)
+        outputs = self.model(images)                       # (pred [N, K], x_part [N, P, C])
+        loss = self.criterion(outputs, labels)
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.allreduce.finish()
+        self.optimizer.step()
+        if slot is not None:
+            slot['free'] = torch.cuda.Event()
+            slot['free'].record()
+        n = images.size(0)
+        self.average_meters['acc'].update(100.0 * float(self.criterion.last_correct.item()) / n, n)
+        self.average_meters['loss'].update(loss.item(), n)
+        return loss
+
+    def batch_validate(self, data):
+        import torch
+        from .train import accuracy
+        images, labels = self.to_device(data['img']), self.to_device(data['label'])
+        with torch.no_grad():
+            pred, _ = self.model(images)
+        self.average_meters['acc'].update(accuracy(pred, labels, 1), images.size(0))
+
+
+TRAINERS = {'BCNN': BCNNTrainer, 'CBCNN': CBCNNTrainer, 'MPN': MPNTrainer, 'PeerLearning': PeerLearningTrainer,
+            'OSMENet': OSMENetTrainer}
 
 
 def main(argv=None):

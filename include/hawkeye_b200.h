@@ -205,6 +205,15 @@ int hk_row_mean_bwd(const float* dy, float* dx, long long rows, int cols, int ld
 int hk_se_gate_fwd(const float* x, const float* m, float* s, long long rows, int hw, void* stream);
 int hk_se_gate_bwd(const float* x, const float* m, const float* ds, float* dx, float* dm, long long rows, int hw,
                    void* stream);
+/* ---- MAMC / N-pairs loss of OSMENet: model/loss/MAMC_loss.py:24-90 -------------------------------------------------------
+ * hk_l2norm_rows_*: F.normalize(p=2, dim=1) of [rows, D] and its backward (inv_norm[r] = 1 / max(||x_r||, 1e-12)).
+ * hk_npair_loss: prod [n,n] = F F^T of the n = batch x attention anchors (row-normalised features), cls[n] / part[n] the
+ * label and attention index of each anchor.  Adds the N-pairs loss (sum of the three terms of eq. 11, divided by n) to the
+ * pre-zeroed fp64 accumulator loss_acc[0] and writes d loss / d prod [n,n].  One launch, O(n) per anchor
+ * (sum_k exp(neg_k - pos_j) = exp(-pos_j) * sum_k exp(neg_k)) instead of the reference's per-anchor Python loop. */
+int hk_l2norm_rows_fwd(const float* x, float* y, float* inv_norm, int rows, int D, void* stream);
+int hk_l2norm_rows_bwd(const float* y, const float* inv_norm, const float* dy, float* dx, int rows, int D, void* stream);
+int hk_npair_loss(const float* prod, const int* cls, const int* part, double* loss_acc, float* dprod, int n, void* stream);
 int hk_relu_fwd(const float* x, float* y, size_t n, void* stream);
 int hk_relu_bwd(const float* y, const float* dy, float* dx, size_t n, void* stream);
 

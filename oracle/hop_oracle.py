@@ -444,3 +444,32 @@ def mpn_forward(x, st, iter_num=5, nl=Plain):
     f = nl.relu(_bn_train(F.conv2d(f, st['pool.conv_dr_block.0.weight']), st, 'pool.conv_dr_block.1'))
     v = _TriuvecFn.apply(_SqrtmFn.apply(_CovpoolFn.apply(f), iter_num))            # MPNCOV.py:97-101
     return F.linear(v.reshape(v.shape[0], -1), st['classifier.weight'], st['classifier.bias'])
+
+
+def npairs_loss(feats, labels):
+    """NPairsLoss.forward (model/loss/MAMC_loss.py:35-90): [b, p, D] features of p attention branches, one label per sample.
+    Anchors = the b*p rows, L2-normalised; for every anchor three log(1 + sum exp(neg - pos)) sums over (positive, negative)
+    sets chosen by same/different attention and same/different class (:50-55), looped over anchors exactly as the reference."""
+    b, p, _ = feats.shape
+    n = b * p
+    x = F.normalize(feats.reshape(n, -1), p=2, dim=1)                                  # :41-43
+    t = torch.repeat_interleave(labels, p)                                             # :44
+    parts = torch.arange(p).repeat(b)                                                  # :45
+    prod = x @ x.t()                                                                   # :46
+    sc = t.expand(n, n).eq(t.expand(n, n).t())                                         # :50
+    sa = parts.expand(n, n).eq(parts.expand(n, n).t())                                 # :51
+    s_sasc, s_sadc, s_dasc, s_dadc = sc & sa, (~sc) & sa, sc & (~sa), (~sc) & (~sa)    # :53-56
+    total = prod.new_zeros(())
+
+    def term(pos, neg):                                                                # :64-70 (and :73-88)
+        return torch.log(1 + torch.exp(neg[None, :] - pos[:, None]).sum(dim=1)).sum()
+    for i in range(n):
+        total = total + term(prod[i][s_sasc[i]], prod[i][s_sadc[i] | s_dasc[i] | s_dadc[i]])
+        total = total + term(prod[i][s_sadc[i]], prod[i][s_dadc[i]])
+        total = total + term(prod[i][s_dasc[i]], prod[i][s_dadc[i]])
+    return total / n                                                                   # :90
+
+
+def mamc_loss(pred, x_part, labels, lambda_a=0.5):
+    """MAMCLoss.forward (MAMC_loss.py:15-21): CE(label_smoothing=0.1) + lambda_a * N-pairs."""
+    return F.cross_entropy(pred, labels, label_smoothing=0.1) + lambda_a * npairs_loss(x_part, labels)

@@ -78,3 +78,25 @@ net = MODEL.get('OSMENet')(rh.cfg(name='OSMENet', num_attention=2, num_classes=2
 out['osme_state_keys_json'] = np.frombuffer(json.dumps({k: list(v.shape) for k, v in net.state_dict().items()}, sort_keys=True).encode(), dtype=np.uint8)
 np.savez_compressed(os.path.join(HERE, 'reference_cin.npz'), **out)
 print('wrote', len(out), 'arrays (with OSME);', os.path.getsize(os.path.join(HERE, 'reference_cin.npz')) / 1e6, 'MB')
+
+# ---- MAMC / N-pairs loss (model/loss/MAMC_loss.py:6-90): the criterion of OSMENet ---------------------------
+from model.loss.MAMC_loss import MAMCLoss, NPairsLoss  # noqa: E402
+
+for tag, b, p, D, ncls in (('npair_b8_p2', 8, 2, 64, 3), ('npair_b12_p3', 12, 3, 32, 4), ('npair_b6_p2_allsame', 6, 2, 16, 1),
+                           ('npair_b4_p2_alldiff', 4, 2, 16, 4)):
+    f = detgen.det((b, p, D), 201).requires_grad_(True)
+    lab = torch.arange(b) % ncls                       # balanced classes, several samples per class (BalancedBatchSampler)
+    loss = NPairsLoss()(f, lab)
+    loss.backward()
+    out[f'{tag}_feats'], out[f'{tag}_labels'] = f.detach().numpy(), lab.numpy()
+    out[f'{tag}_loss'], out[f'{tag}_dfeats'] = np.float64(loss.item()), f.grad.numpy()
+crit = MAMCLoss(rh.cfg(lambda_a=0.5, use_mamc=True))
+pred = detgen.det((8, 200), 202).requires_grad_(True)
+parts = detgen.det((8, 2, 64), 203).requires_grad_(True)
+lab = torch.arange(8) % 3
+loss = crit((pred, parts), lab)
+loss.backward()
+out['mamc_pred'], out['mamc_parts'], out['mamc_labels'] = pred.detach().numpy(), parts.detach().numpy(), lab.numpy()
+out['mamc_loss'], out['mamc_dpred'], out['mamc_dparts'] = np.float64(loss.item()), pred.grad.numpy(), parts.grad.numpy()
+np.savez_compressed(os.path.join(HERE, 'reference_cin.npz'), **out)
+print('wrote', len(out), 'arrays (with OSME + MAMC);', os.path.getsize(os.path.join(HERE, 'reference_cin.npz')) / 1e6, 'MB')

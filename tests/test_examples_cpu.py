@@ -51,4 +51,16 @@ def test_bcnn_stages():
     assert _groups(t1) == [(52429000, 1.0)]                               # Examples/BCNN.py:35-36
     t2 = _bare(examples.BCNNTrainer, load_config(os.path.join(REPO, 'configs', 'BCNN_S2.yaml')))
     assert sum(n for n, _ in _groups(t2)) == 67143688                     # :38-39
-    assert set(examples.TRAINERS) == {'BCNN', 'CBCNN', 'MPN', 'PeerLearning'}
+    assert set(examples.TRAINERS) == {'BCNN', 'CBCNN', 'MPN', 'PeerLearning', 'OSMENet'}
+
+
+def test_osmenet_param_groups_and_criterion(monkeypatch):
+    monkeypatch.setenv('HAWKEYE_ALLOW_RANDOM_INIT', '1')
+    cfg = load_config(os.path.join(REPO, 'configs', 'OSMENet.yaml'))
+    t = _bare(examples.OSMENetTrainer, cfg)
+    g = _groups(t)                                                        # Examples/OSMENet.py:35-42: backbone 0.1 x lr
+    assert [m for _, m in g] == [0.1, 1.0]
+    n_backbone = sum(p.numel() for p in t.model.backbone.parameters())
+    assert g[0][0] == n_backbone and sum(n for n, _ in g) == sum(p.numel() for p in t.model.parameters())
+    crit = t.get_criterion(cfg.train.criterion)
+    assert crit.lambda_a == 0.5 and crit.use_mamc is True                 # MAMC_loss.py:9-10
