@@ -45,6 +45,9 @@ WORKLOADS = {
     'bcnn_s1': dict(cfg='BCNN_S1.yaml', trainer='BCNN', model='BCNN VGG-16 stage 1 (classifier only)', fwd_gflop=VGG16_FWD_GFLOP_PER_IMG, bwd_mult=1.0),
     'cbcnn8192': dict(cfg='CBCNN_S1.yaml', trainer='CBCNN', model='CBCNN VGG-16 d=8192 stage 1', fwd_gflop=VGG16_FWD_GFLOP_PER_IMG, bwd_mult=1.0),
     'mpn': dict(cfg='MPN.yaml', trainer='MPN', model='Fast MPN-COV ResNet-50', fwd_gflop=RESNET50_MPN_FWD_GFLOP_PER_IMG, bwd_mult=3.0),
+    # BASELINE.json config 5 (OSME half): ResNet-101 trunk (4 x 7.8 GFLOP at 448x448) + two 401408 -> 1024 attention FCs; MAMC loss
+    'osmenet': dict(cfg='OSMENet.yaml', trainer='OSMENet', model='OSMENet ResNet-101 + OSME (2 attentions) + MAMC loss',
+                    fwd_gflop=32.9, bwd_mult=3.0),
 }
 
 
@@ -543,9 +546,12 @@ def main():
         except Exception as e:          # e.g. out of memory next to a large resident workload
             line['eager_gpu'] = {'unavailable': repr(e)[:200]}
     if not args.no_cpu_baseline:
-        cb = cpu_baseline(args.workload, 2)
-        cb.pop('dt')
-        line['cpu_baseline'] = cb
+        if args.workload == 'osmenet':     # the reference OSME hard-codes a 7x7 map (OSME.py:57): it cannot run at 448x448
+            line['cpu_baseline'] = {'unavailable': 'reference OSMENet is fixed to 224x224 inputs (OSME.py:57)'}
+        else:
+            cb = cpu_baseline(args.workload, 2)
+            cb.pop('dt')
+            line['cpu_baseline'] = cb
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

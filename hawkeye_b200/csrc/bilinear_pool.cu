@@ -524,6 +524,34 @@ __global__ void norm_from_s_kernel(const float* s, float* inv_norm, int C, int H
   }
 }
 
+// colsum_finish + norm_from_s + bilinear_bwd_scalars in one launch (one block per image, after the S kernel):
+//   s[b][p] = sum over splits of partial;  n = sqrt(sum_p s_p^2 / HW + C^2 eps);  alpha = 1/(n HW);  beta = -(c_raw/n^2)/(n HW)
+__global__ void bilinear_bwd_finish_kernel(const float* __restrict__ partial, float* __restrict__ s, float* __restrict__ inv_norm,
+                                           const double* __restrict__ c_raw, float* __restrict__ alpha, float* __restrict__ beta,
+                                           int CS, int C, int HW, float inv_hw) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float acc = 0.f;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    float t = 0.f;
+    for (int cs = 0; cs < CS; ++cs) t += partial[((size_t)b * CS + cs) * HW + p];
+    s[(size_t)b * HW + p] = t;
+    acc = fmaf(t, t, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    const float nrm = sqrtf(t * inv_hw + (float)C * (float)C * 1e-5f);
+    const float in = 1.f / fmaxf(nrm, 1e-12f);
+    inv_norm[b] = in;
+    alpha[b] = in * inv_hw;
+    beta[b] = -((float)c_raw[b] * in * in) * in * inv_hw;
+  }
+}
+
 }  // namespace hk
 
 namespace hk {
@@ -677,18 +705,14 @@ static int bilinear_bwd_impl(const float* x, const float* dy, float* dx, int B, 
   colsum_partial_kernel<<<dim3(B, COLSUM_SPLITS), 256, colsum_smem(HW), stream>>>(x, partial, C, HW, COLSUM_SPLITS,
                                                                                 reinterpret_cast<float*>(craw), nullptr, 2);
   HK_LAUNCH_CHECK("colsum_partial_kernel");
-  // s_p = sum_c x_cp (also the rank-1 correction vector of the backward); the norm follows in closed form
-  colsum_finish_kernel<<<B, 256, 0, stream>>>(partial, svec, COLSUM_SPLITS, HW);
-  HK_LAUNCH_CHECK("colsum_finish_kernel");
   GramArgs a = {};
   a.B = B; a.C = C; a.HW = HW; a.nblk = C / 128;
   a.inv_hw = inv_hw; a.eps = 1e-5f;
   a.dY = dy; a.S = S; a.c_raw = craw;
   if ((r = launch_gram<MODE_BCNN_BWD_S>(tm, a, stream))) return r;
-  norm_from_s_kernel<<<B, 256, 0, stream>>>(svec, invn, C, HW, inv_hw);
-  HK_LAUNCH_CHECK("norm_from_s_kernel");
-  bilinear_bwd_scalars_kernel<<<(B + 127) / 128, 128, 0, stream>>>(invn, craw, inv_hw, alpha, beta, B);
-  HK_LAUNCH_CHECK("bilinear_bwd_scalars_kernel");
+  // s_p = sum_c x_cp (the rank-1 correction vector of the backward), the closed-form norm and the epilogue scalars: one launch
+  bilinear_bwd_finish_kernel<<<B, 256, 0, stream>>>(partial, svec, invn, craw, alpha, beta, COLSUM_SPLITS, C, HW, inv_hw);
+  HK_LAUNCH_CHECK("bilinear_bwd_finish_kernel");
   // dX = alpha_b * (S . X) + beta_b * 1 s^T      (M=C, K=C, N=HW; X is the MN-major B operand); rounded to tf32: it is
   // the dY operand of the last conv's dgrad / wgrad MMAs
   return hk_gemm_tf32(S, 0, C, (long long)C * C, x, 1, HW, (long long)C * HW, dx, HW, (long long)C * HW, 0, C, HW, C, B,
