@@ -66,6 +66,25 @@ def test_full_batch_properties():
         ops.bilinear_pool(torch.rand(1, 100, 4, 4, device='cuda'))
 
 
+def test_baseline_batch_elementwise_vs_oracle():
+    """BASELINE size (B=32, C=512, 14x14; the super-tile / cluster kernel) and the first size past one wave of clusters
+    (B=40: tile kernel), forward AND backward, element-wise against the fp64 oracle, per image."""
+    from hawkeye_b200 import ops
+    from oracle import hop_oracle as O
+    for B in (32, 40):
+        x = torch.relu(detgen.det_uniform((B, 512, 14, 14), 31) - 0.2)       # sparse, non-negative: what a ReLU + pool stack emits
+        dy = detgen.det((B, 512 * 512), 32)
+        xg = x.cuda().requires_grad_(True)
+        y = ops.bilinear_pool(xg)
+        (dx,) = torch.autograd.grad(y, xg, dy.cuda())
+        y_ref = O.bilinear_pool_fwd(x.double())
+        dx_ref = O.bilinear_pool_bwd(x.double(), dy.double())
+        wf = max(rel_l2(y[b].detach().cpu(), y_ref[b]) for b in range(B))
+        wb = max(rel_l2(dx[b].cpu(), dx_ref[b]) for b in range(B))
+        print(f'bilinear B={B}: worst image fwd {wf:.2e} bwd {wb:.2e}')
+        assert wf < 1e-3 and wb < 2e-3
+
+
 @pytest.mark.parametrize('env', [{'HK_K1': 'tiles', 'HK_K1_POLL_LIMIT': '0'}, {'HK_K1': 'tiles'}, {'HK_K1': 'cluster'}, {'HK_K1': 'two'},
                                  {'HK_K1': 'super'}, {'HK_K1': 'super', 'HK_K1_SUPER_CL': '0'},
                                  {'HK_K1': 'super', 'HK_K1_SUPER_CL': '0', 'HK_K1_POLL_LIMIT': '0'}])
