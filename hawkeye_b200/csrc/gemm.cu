@@ -191,7 +191,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const long long ldE = epi.ldE ? epi.ldE : epi.ldc;
       const float* Eb = epi.E ? epi.E + (long long)bz * (epi.ldE ? epi.strideE : epi.strideC) : nullptr;
       float* Clb = epi.C_lo ? epi.C_lo + (long long)bz * epi.strideC : nullptr;
-      const bool simple = !Eb && !Db && !Clb && epi.diag == 0.f && !epi.trans_c;
+      const bool simple = !Eb && !Clb && !Dlb && epi.diag == 0.f && !epi.trans_c && (!Db || epi.ldd != 0);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         float v[32];
@@ -207,29 +207,41 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int col0 = n0 + c * 32;
         // fast path (plain scaled store of a full, aligned 32-column chunk): a handful of instructions per element — the
         // general path below costs ~60 and dominates short-K GEMMs such as the first VGG layer (K = 32)
-        if (simple && col0 + 32 <= N && (epi.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cb) & 15) == 0) {
+        if (simple && col0 + 32 <= N && (epi.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cb) & 15) == 0 &&
+            (!Db || ((epi.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(Db) & 15) == 0))) {
           // A thread owns 32 consecutive columns of ONE row, so a direct float4 store instruction would touch 32 rows x 16 B —
           // half-written 32 B sectors, twice the L2 write transactions (the 1x1-conv GEMMs of the ResNet trunk are
           // output-write-bound).  Transpose the 32 x 32 chunk through a warp-private shared-memory tile instead: every store
-          // instruction then writes four full 128 B rows.
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float o = alpha * v[j];
-            if (epi.relu & 1) o = fmaxf(o, 0.f);
-            if (epi.relu & 2) o = tf32_round(o);
-            v[j] = o;
-          }
+          // instruction then writes four full 128 B rows; the optional addend D (residual gradient) is read the same way.
           float* tile = epi_tiles + (warp - 2) * (32 * 36);
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(tile + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            *reinterpret_cast<float4*>(tile + lane * 36 + j) =
+                make_float4(alpha * v[j], alpha * v[j + 1], alpha * v[j + 2], alpha * v[j + 3]);
           __syncwarp();
           const int row0 = m0 + q * 32;
+          float4 dadd[8];
+          if (Db) {      // all eight addend loads in flight before the first store (C and D may alias as far as the compiler knows)
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + (lane >> 3);
+              dadd[it] = (row0 + r < M) ? __ldg(reinterpret_cast<const float4*>(Db + (long long)(row0 + r) * epi.ldd + col0 + (lane & 7) * 4))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + (lane >> 3);
-            const float4 t = *reinterpret_cast<const float4*>(tile + r * 36 + (lane & 7) * 4);
-            if (row0 + r < M) *reinterpret_cast<float4*>(Cb + (long long)(row0 + r) * epi.ldc + col0 + (lane & 7) * 4) = t;
+            float4 t = *reinterpret_cast<const float4*>(tile + r * 36 + (lane & 7) * 4);
+            if (row0 + r < M) {
+              if (Db) {
+                const float4 d = dadd[it];
+                t.x = fmaf(beta, d.x, t.x); t.y = fmaf(beta, d.y, t.y); t.z = fmaf(beta, d.z, t.z); t.w = fmaf(beta, d.w, t.w);
+              }
+              if (epi.relu & 1) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+              if (epi.relu & 2) { t.x = tf32_round(t.x); t.y = tf32_round(t.y); t.z = tf32_round(t.z); t.w = tf32_round(t.w); }
+              *reinterpret_cast<float4*>(Cb + (long long)(row0 + r) * epi.ldc + col0 + (lane & 7) * 4) = t;
+            }
           }
           __syncwarp();
           continue;

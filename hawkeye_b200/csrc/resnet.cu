@@ -366,9 +366,16 @@ static int bn_blocks(long long P) {
   if (b < 1) b = 1;
   return (int)b;
 }
-static int kc_splits(long long P) {
-  for (int S = 296; S > 1; --S)
-    if (P % S == 0 && P / S >= 64) return S;
+// split-K factor of the 1x1-conv weight gradient dW[Cout][K] = dY^T . X over P pixels: just enough splits to fill the SMs about
+// twice with 128 x BN output tiles (the partial sums cost S x Cout x K floats of write + read: with the former "as many as divide
+// P" rule a 2048x512 layer moved 0.4 GB per call through the reduction), each split at least 64 pixels long; S divides P.
+static int kc_splits(long long P, int Cout, int K) {
+  const int BN = K <= 64 ? 64 : (K <= 128 ? 128 : 256);
+  const long long tiles = (long long)((Cout + 127) / 128) * ((K + BN - 1) / BN);
+  long long target = (296 + tiles - 1) / tiles;
+  if (target > 296) target = 296;
+  for (long long S = target; S > 1; --S)
+    if (P % S == 0 && P / S >= 64) return (int)S;
   return 1;
 }
 
@@ -504,7 +511,7 @@ int hk_nchw_to_nhwc(const float* x, float* y, int N, int HW, int C, void* stream
 /* weight gradient of a matrix-form (1x1 / im2col) convolution: dw [Cout][K] = dY[P][Cout]^T . X[P][K], split-K batched
  * MN-major tcgen05 GEMM + reduction.  workspace = S * Cout * K floats. */
 size_t hk_matconv_wgrad_workspace_bytes(long long P, int K, int Cout) {
-  return (size_t)kc_splits(P) * Cout * K * sizeof(float);
+  return (size_t)kc_splits(P, Cout, K) * Cout * K * sizeof(float);
 }
 int hk_matconv_wgrad(const float* x, const float* dy, float* dw, long long P, int K, int Cout, void* workspace,
                      size_t workspace_bytes, void* stream_) {
@@ -513,7 +520,7 @@ int hk_matconv_wgrad(const float* x, const float* dy, float* dw, long long P, in
   HK_REQUIRE(K % 4 == 0 && Cout % 4 == 0, HK_ERR_UNSUPPORTED, "hk_matconv_wgrad: K=%d Cout=%d must be multiples of 4", K, Cout);
   HK_REQUIRE(workspace && workspace_bytes >= hk_matconv_wgrad_workspace_bytes(P, K, Cout), HK_ERR_WORKSPACE,
              "hk_matconv_wgrad: workspace too small");
-  const int S = kc_splits(P);
+  const int S = kc_splits(P, Cout, K);
   const long long Kc = P / S;
   float* part = static_cast<float*>(workspace);
   GemmEpi e = {};

@@ -12,9 +12,10 @@ from .ops import _check_cuda, _f32c, _ws
 BN_EPS = 1e-5
 
 
-def _gemm(A, a_mn, lda, B, b_mn, ldb, C, ldc, M, N, K, relu=0):
-    _lib.call('hk_gemm_tf32', A, int(a_mn), lda, 0, B, int(b_mn), ldb, 0, C, ldc, 0, 0, M, N, K, 1, 1.0, None, 0.0, None,
-              0, 0, 0.0, None, relu, _lib.stream_ptr())
+def _gemm(A, a_mn, lda, B, b_mn, ldb, C, ldc, M, N, K, relu=0, D=None):
+    """C = A.B (+ D, same layout as C: the residual-gradient add rides in the GEMM epilogue instead of a separate pass)"""
+    _lib.call('hk_gemm_tf32', A, int(a_mn), lda, 0, B, int(b_mn), ldb, 0, C, ldc, 0, 0, M, N, K, 1, 1.0, None, 0.0, D,
+              ldc if D is not None else 0, 0, 1.0 if D is not None else 0.0, None, relu, _lib.stream_ptr())
 
 
 class Unit:
@@ -93,7 +94,8 @@ class Unit:
         return y, None
 
     # ---- backward: dy NHWC -> (dx NHWC or None, dres or None, dw, dgamma, dbeta)
-    def backward(self, rec, dy, need_dx=True):
+    def backward(self, rec, dy, need_dx=True, addend=None):
+        """addend (optional, same shape as dx): added to dx — inside the dgrad GEMM's epilogue for 1x1 convs"""
         s = _lib.stream_ptr()
         dev = dy.device
         P, cout = rec['P'], rec['cout']
@@ -121,7 +123,10 @@ class Unit:
             _lib.call('hk_matconv_wgrad', xin, dc, dw, P, cin, cout, wsb, wsb.numel(), s)
             if need_dx:
                 dxs = torch.empty_like(xin)
-                _gemm(dc, 0, cout, w, 1, cin, dxs, cin, P, cin, cout)       # dX = dC . W   (W [Cout,Cin] as the MN-major B)
+                fused = addend if (addend is not None and self.kind == '1x1') else None
+                _gemm(dc, 0, cout, w, 1, cin, dxs, cin, P, cin, cout, D=fused)   # dX = dC . W (+ addend)  (W [Cout,Cin] as the MN-major B)
+                if fused is not None:
+                    addend = None
                 if self.kind == '1x1s2':
                     H, W = rec['full_hw']
                     dx = torch.empty(N, H, W, cin, device=dev, dtype=torch.float32)
@@ -141,6 +146,8 @@ class Unit:
             if need_dx:
                 dx = torch.empty(N, H, W, cin, device=dev, dtype=torch.float32)
                 _lib.call('hk_conv3x3_dgrad', g, rec['wd'], None, dx, N, H, W, cin, cout, s)
+        if addend is not None and dx is not None:
+            dx = _add(dx, addend)
         return dx, dres, dw, dgamma, dbeta
 
 
@@ -232,14 +239,15 @@ class ResNetTrunkFn(Function):
         for (u1, u2, u3, ds), (_, (r1, r2, r3, rd), _) in zip(reversed(plan.blocks), reversed(recs[1:])):
             d2, dres, dw3, dg3, db3 = u3.backward(r3, g)
             d1, _, dw2, dg2, db2 = u2.backward(r2, d2)
-            dx, _, dw1, dg1, db1 = u1.backward(r1, d1)
-            blk = [(dw1, dg1, db1), (dw2, dg2, db2), (dw3, dg3, db3)]
+            # the identity branch's gradient (dres, or the downsample unit's dx) is added inside u1's dgrad GEMM epilogue
+            extra = None
             if ds is not None:
                 dxd, _, dwd, dgd, dbd = ds.backward(rd, dres)
-                dx = _add(dx, dxd)
-                blk.append((dwd, dgd, dbd))
-            else:
-                dx = _add(dx, dres)
+                extra = (dwd, dgd, dbd)
+            dx, _, dw1, dg1, db1 = u1.backward(r1, d1, addend=dxd if ds is not None else dres)
+            blk = [(dw1, dg1, db1), (dw2, dg2, db2), (dw3, dg3, db3)]
+            if extra is not None:
+                blk.append(extra)
             grads = blk + grads
             g = dx
         _, r0, (yshape, am) = recs[0]
