@@ -42,7 +42,7 @@ def summarize(so_path):
         if not keys:
             simt += 1
             continue
-        short = re.sub(r'\(.*', '', name).replace('void ', '').replace('hk::', '')
+        short = re.sub(r'\(.*', '', name.replace('(anonymous namespace)::', '')).replace('void ', '').replace('hk::', '')
         lines.append(f'{short:60s} ' + ' '.join(f'{k}={c[k]}' for k in sorted(c)))
     lines.append(f'# + {simt} SIMT kernels (elementwise / reductions / layout) without tensor-core or TMA instructions')
     return '\n'.join(lines) + '\n'
