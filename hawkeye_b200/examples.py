@@ -60,6 +60,22 @@ class OSMENetTrainer(Trainer):
     The reference draws class-balanced batches (dataset/sampler.py BalancedBatchSampler: n_classes x n_samples) so that every
     anchor has same-class partners; with a user-supplied dataloader that is the caller's business, as in the reference."""
 
+    def get_dataloader(self, config):
+        """Examples/OSMENet.py:17-30: the training loader draws class-balanced batches (n_classes x n_samples images)."""
+        import numpy as np
+        from torch.utils.data import DataLoader
+        loaders = super().get_dataloader(config)                 # datasets, transforms, validation loader
+        try:
+            from dataset.sampler import BalancedBatchSampler
+        except Exception:
+            from .data import BalancedBatchSampler
+        if self.world > 1:                                       # one process per GPU: each rank draws its own balanced batches
+            np.random.seed((self.config.experiment.seed if 'seed' in self.config.experiment else 0) + self.rank)
+        sampler = BalancedBatchSampler(self.datasets['train'], config.n_classes, config.n_samples)
+        loaders['train'] = DataLoader(self.datasets['train'], num_workers=config.num_workers, pin_memory=True,
+                                      batch_sampler=sampler)
+        return loaders
+
     def get_criterion(self, config):
         from .losses import MAMCLoss
         return MAMCLoss(config)

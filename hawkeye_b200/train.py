@@ -107,13 +107,12 @@ class Trainer:
         return model
 
     def get_dataloader(self, config):
-        try:
-            from dataset.dataset import FGDataset  # noqa: F401  (reference package, when run inside Hawkeye)
-        except Exception as e:
-            raise RuntimeError('the image input pipeline is outside this package: pass dataloaders= or run inside a '
-                               'Hawkeye checkout') from e
+        try:        # inside a Hawkeye checkout: the reference's own classes; otherwise the mirror in hawkeye_b200.data
+            from dataset.dataset import FGDataset
+            from dataset.transforms import ClassificationPresetTrain, ClassificationPresetEval
+        except Exception:
+            from .data import FGDataset, ClassificationPresetTrain, ClassificationPresetEval
         from torch.utils.data import DataLoader
-        from dataset.transforms import ClassificationPresetTrain, ClassificationPresetEval
         t = config.transformer
         resize = t['resize_size'] if 'resize_size' in t else int(t['image_size'] / 0.875)
         tf = {'train': ClassificationPresetTrain(crop_size=t['image_size'], auto_augment_policy='ta_wide',
@@ -121,6 +120,7 @@ class Trainer:
               'val': ClassificationPresetEval(crop_size=t['image_size'], resize_size=resize)}
         ds = {s: FGDataset(config.root_dir, os.path.join(config.meta_dir, s + '.txt'), transform=tf[s])
               for s in ('train', 'val')}
+        self.datasets = ds
         # One process per GPU replaces nn.DataParallel (train.py:220-228), which SPLITS config.batch_size across the visible
         # GPUs: batch_size stays the GLOBAL batch, each rank draws batch_size / world images from its own shard of the
         # training set (DistributedSampler, reshuffled per epoch in train()); validation is sharded the same way and the
