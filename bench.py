@@ -230,6 +230,9 @@ def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    if args.workload == 'osmenet':      # the reference OSME hard-codes a 7x7 trunk output (OSME.py:57): no 448x448 reference step exists
+        print(json.dumps({'impl': 'reference', 'unavailable': 'reference OSMENet is fixed to 224x224 inputs (OSME.py:57)'}), flush=True)
+        return
     timed = max(1, min(args.steps, 3))
     cb = cpu_baseline(args.workload, timed)
     dt = cb.pop('dt')

@@ -47,6 +47,9 @@ class NPairsLossFn(Function):
         _check_cuda(feats, labels)
         b, p, D = feats.shape
         n = b * p
+        if n % 4 or D % 4:
+            raise _lib.HawkeyeLibError(f'NPairsLoss: batch x attentions = {n} and the feature size {D} must be multiples of 4 '
+                                       '(16-byte TMA row pitch of the anchor-similarity GEMMs)')
         x = _f32c(feats).reshape(n, D)
         s = _lib.stream_ptr()
         dev = x.device
