@@ -71,3 +71,25 @@ def test_errors_are_thread_local_text(lib):
     t = threading.Thread(target=lambda: seen.append(lib.hk_last_error().decode()))
     t.start(); t.join()
     assert 'multiple of 128' in msg and seen == ['']
+
+
+def test_round2_entry_points_argument_errors(lib):
+    """hk_conv3x3_fwd_pool, hk_bn_bwd_ex, hk_l2norm_rows_*, hk_npair_loss: bad arguments are rejected before any launch."""
+    p = lib.hk_conv3x3_fwd_pool
+    assert p(FAKE, FAKE, None, None, None, 2, 8, 8, 64, 64, 0, None) == -1 and 'null output' in err(lib)
+    assert p(FAKE, FAKE, None, FAKE, None, 2, 7, 8, 64, 64, 0, None) == -3 and 'even H/W' in err(lib)
+    assert p(FAKE, FAKE, None, FAKE, FAKE + 8, 2, 8, 8, 64, 64, 0, None) == -3            # unaligned code buffer
+    assert p(FAKE, FAKE, None, FAKE, None, 2, 8, 8, 48, 64, 0, None) == -3 and 'multiples of 32' in err(lib)
+    lib.hk_set_precise(1)
+    try:
+        assert p(FAKE, FAKE, None, FAKE, None, 2, 8, 8, 64, 64, 0, None) == -3 and '3xTF32' in err(lib)
+    finally:
+        lib.hk_set_precise(0)
+    b = lib.hk_bn_bwd_ex
+    assert b(FAKE, None, FAKE, FAKE, None, FAKE, FAKE, FAKE, None, FAKE, FAKE, 64, 64, 1, FAKE, 1 << 30, None) == -1  # relu needs y or beta
+    assert b(FAKE, None, FAKE, FAKE, FAKE, FAKE, FAKE, FAKE, None, FAKE, FAKE, 64, 62, 1, FAKE, 1 << 30, None) == -3
+    assert b(FAKE, None, FAKE, FAKE, FAKE, FAKE, FAKE, FAKE, None, FAKE, FAKE, 64, 64, 1, FAKE, 16, None) == -4
+    assert lib.hk_l2norm_rows_fwd(None, FAKE, FAKE, 4, 64, None) == -1
+    assert lib.hk_l2norm_rows_bwd(FAKE, FAKE, None, FAKE, 4, 64, None) == -1
+    assert lib.hk_npair_loss(FAKE, FAKE, FAKE, None, FAKE, 8, None) == -1
+    assert lib.hk_npair_loss(FAKE, FAKE, FAKE, FAKE, FAKE, 0, None) == -1
